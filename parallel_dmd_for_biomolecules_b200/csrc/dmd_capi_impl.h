@@ -1,0 +1,463 @@
+// dmd_capi_impl.h -- the C ABI of include/dmdb200.h, written once against a tiny backend namespace `be`
+// (allocation, copies, and one launcher per device operation).  Included by
+//   dmd_cuda.cu                      -> libdmdb200.so (the product: CUDA backend, sm_100a kernels)
+//   tests/host_trace/trace_lib.cpp   -> test-only 1-lane CPU trace of the same engine source (never shipped)
+// The including file must define namespace be { init, alloc, release, h2d, d2h, fill_i32, run_op, ... }.
+#pragma once
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/dmdb200.h"
+#include "dmd_host.h"
+#include "dmd_types.h"
+
+namespace dmd {
+enum Op { OP_START = 0, OP_NBOR, OP_PREDICT_ALL, OP_RUN, OP_SYNC_POS, OP_ENERGY, OP_EVCODE };
+}
+
+static thread_local std::string g_create_error;
+
+struct dmdb_handle {
+  dmd::HostModel model;
+  dmd::DevArrays d;
+  std::vector<void*> allocs;
+  std::vector<double> tstar;  // per replica
+  std::vector<char> loaded;   // per replica: dmdb_set_state done
+  dmd::OutRec* eout = nullptr;   // device: n_replicas
+  int32_t* pair_buf = nullptr;   // device scratch for dmdb_get_evcode
+  size_t pair_cap = 0;
+  std::string err;
+  double last_ms = 0;
+  int last_launches = 0;
+};
+
+namespace {
+
+template <class T>
+T* dalloc(dmdb_handle* h, size_t n) {
+  void* p = be::alloc(n * sizeof(T));
+  h->allocs.push_back(p);
+  return (T*)p;
+}
+
+int fail(dmdb_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+#define DMDB_TRY(h, ...)                                   \
+  try {                                                    \
+    __VA_ARGS__                                            \
+  } catch (const std::exception& e) {                      \
+    return fail(h, DMDB_ERR_CUDA, e.what());               \
+  }
+
+int check_replica(dmdb_handle* h, int replica, bool need_loaded) {
+  if (!h) return DMDB_ERR_ARG;
+  if (replica < 0 || replica >= h->d.n_replicas) return fail(h, DMDB_ERR_ARG, "replica index out of range");
+  if (need_loaded && !h->loaded[replica]) return fail(h, DMDB_ERR_STATE, "dmdb_set_state has not been called for this replica");
+  return 0;
+}
+
+int all_loaded(dmdb_handle* h) {
+  if (!h) return DMDB_ERR_ARG;
+  for (char c : h->loaded)
+    if (!c) return fail(h, DMDB_ERR_STATE, "dmdb_set_state has not been called for every replica");
+  return 0;
+}
+
+const char* device_error_text(int e) {
+  switch (e) {
+    case dmd::DMD_E_NBR_CAP: return "neighbour list capacity exceeded (raise dmdb_params.nbr_capacity)";
+    case dmd::DMD_E_CAL_EMPTY: return "event calendar empty";
+    case dmd::DMD_E_NEG_TIME: return "negative event time";
+    case dmd::DMD_E_GRID: return "bead outside the cell grid";
+  }
+  return "unknown device error";
+}
+
+// after a device op: surface device-side error words
+int check_device_errors(dmdb_handle* h) {
+  const int R = h->d.n_replicas;
+  std::vector<dmd::RepScalars> sc(R);
+  be::d2h(sc.data(), h->d.scal, sizeof(dmd::RepScalars) * R);
+  for (int r = 0; r < R; r++)
+    if (sc[r].error) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "replica %d: %s (info %d)", r, device_error_text(sc[r].error), sc[r].error_info);
+      int code = sc[r].error == dmd::DMD_E_NBR_CAP ? DMDB_ERR_CAPACITY : DMDB_ERR_PHYSICS;
+      return fail(h, code, buf);
+    }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dmdb_create(const dmdb_params* p, const dmdb_topology* topo, const dmdb_tables* tab, dmdb_handle** out) {
+  if (!p || !topo || !tab || !out) return fail(nullptr, DMDB_ERR_ARG, "null argument");
+  if (p->n_replicas < 1) return fail(nullptr, DMDB_ERR_ARG, "n_replicas must be >= 1");
+  std::string err;
+  if (!be::init(p->device, err)) return fail(nullptr, DMDB_ERR_NO_DEVICE, err);
+  std::unique_ptr<dmdb_handle> h(new dmdb_handle());
+  try {
+    dmd::build_model(*p, *topo, *tab, h->model);
+  } catch (const std::exception& e) {
+    return fail(nullptr, DMDB_ERR_ARG, e.what());
+  }
+  try {
+    const dmd::SysConst& s = h->model.sys;
+    const size_t R = (size_t)p->n_replicas, N = (size_t)s.N;
+    dmd::DevArrays& d = h->d;
+    std::memset(&d, 0, sizeof(d));
+    d.n_replicas = (int)R;
+    d.tim_stride = s.ngroups * 32;
+    dmd::SysConst* dsys = dalloc<dmd::SysConst>(h.get(), 1);
+    be::h2d(dsys, &s, sizeof(s));
+    d.sys = dsys;
+    dmd::PairTables* dtab = dalloc<dmd::PairTables>(h.get(), 1);
+    be::h2d(dtab, &h->model.tab, sizeof(dmd::PairTables));
+    d.tables = dtab;
+    uint32_t* dmeta = dalloc<uint32_t>(h.get(), N);
+    be::h2d(dmeta, h->model.meta.data(), N * 4);
+    d.meta = dmeta;
+    int32_t* dchain = dalloc<int32_t>(h.get(), N);
+    be::h2d(dchain, h->model.chain.data(), N * 4);
+    d.chain = dchain;
+    d.rec = dalloc<dmd::BeadRec>(h.get(), R * N);
+    d.tim = dalloc<double>(h.get(), R * d.tim_stride);
+    d.nptnr = dalloc<int32_t>(h.get(), R * (N + 3));
+    d.ctype = dalloc<int8_t>(h.get(), R * (N + 3));
+    d.er34 = dalloc<int32_t>(h.get(), R * 2 * N);
+    d.up = dalloc<uint32_t>(h.get(), R * N * s.cap);
+    d.dn = dalloc<uint32_t>(h.get(), R * N * s.cap);
+    d.nup = dalloc<uint16_t>(h.get(), R * N);
+    d.ndn = dalloc<uint16_t>(h.get(), R * N);
+    d.oldr = dalloc<double>(h.get(), R * 3 * N);
+    const size_t nc3 = (size_t)s.ncr * s.ncr * s.ncr;
+    d.cellhead = dalloc<int32_t>(h.get(), R * nc3);
+    be::fill_i32(d.cellhead, -1, R * nc3);
+    d.cnext = dalloc<int32_t>(h.get(), R * N);
+    d.cellof = dalloc<int32_t>(h.get(), R * N);
+    d.tmin1 = dalloc<double>(h.get(), R * s.ngroups);
+    d.scal = dalloc<dmd::RepScalars>(h.get(), R);
+    d.log = dalloc<dmd::EventLogRec>(h.get(), R * (size_t)std::max(s.log_cap, 1));
+    d.out = dalloc<dmd::OutRec>(h.get(), R * (size_t)s.out_cap);
+    h->eout = dalloc<dmd::OutRec>(h.get(), R);
+    be::zero(d.nup, R * N * 2);
+    be::zero(d.ndn, R * N * 2);
+    h->tstar.assign(R, p->tstar);
+    h->loaded.assign(R, 0);
+    std::vector<dmd::RepScalars> sc(R);
+    std::memset(sc.data(), 0, sizeof(dmd::RepScalars) * R);
+    be::h2d(d.scal, sc.data(), sizeof(dmd::RepScalars) * R);
+  } catch (const std::exception& e) {
+    for (void* q : h->allocs) be::release(q);
+    return fail(nullptr, DMDB_ERR_CUDA, e.what());
+  }
+  *out = h.release();
+  return DMDB_OK;
+}
+
+void dmdb_destroy(dmdb_handle* h) {
+  if (!h) return;
+  for (void* q : h->allocs) be::release(q);
+  if (h->pair_buf) be::release(h->pair_buf);
+  delete h;
+}
+
+const char* dmdb_last_error(const dmdb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+int dmdb_num_beads(const dmdb_handle* h) { return h ? h->model.sys.N : -1; }
+int dmdb_num_cells(const dmdb_handle* h) { return h ? h->model.sys.num_cell : -1; }
+
+static int upload_replica(dmdb_handle* h, int r, const double* sv, const int32_t* bptnr) {
+  const dmd::SysConst& s = h->model.sys;
+  const size_t N = (size_t)s.N, rr = (size_t)r;
+  dmd::HostReplicaInit init;
+  dmd::build_replica_init(h->model, sv, bptnr, h->tstar[r], h->model.params.seed + (uint64_t)r, h->d.tim_stride, init);
+  dmd::DevArrays& d = h->d;
+  be::h2d(d.rec + rr * N, init.rec.data(), N * sizeof(dmd::BeadRec));
+  be::h2d(d.er34 + rr * 2 * N, init.er34.data(), 2 * N * 4);
+  be::h2d(d.oldr + rr * 3 * N, init.oldr.data(), 3 * N * 8);
+  be::h2d(d.tim + rr * d.tim_stride, init.tim.data(), (size_t)d.tim_stride * 8);
+  be::h2d(d.nptnr + rr * (N + 3), init.nptnr.data(), (N + 3) * 4);
+  be::h2d(d.ctype + rr * (N + 3), init.ctype.data(), (N + 3));
+  be::h2d(d.scal + rr, &init.scal, sizeof(dmd::RepScalars));
+  h->loaded[r] = 1;
+  return 0;
+}
+
+int dmdb_set_state(dmdb_handle* h, int replica, const double* sv, const int32_t* bptnr) {
+  if (!h || !sv) return fail(h, DMDB_ERR_ARG, "null argument");
+  if (replica != -1) {
+    int rc = check_replica(h, replica, false);
+    if (rc) return rc;
+  }
+  try {
+    const int r0 = replica < 0 ? 0 : replica, r1 = replica < 0 ? h->d.n_replicas : replica + 1;
+    for (int r = r0; r < r1; r++) upload_replica(h, r, sv, bptnr);
+    be::run_op(h->d, dmd::OP_START, r0, r1 - r0, 0, nullptr, nullptr, &h->last_ms, &h->last_launches);
+  } catch (const std::exception& e) {
+    return fail(h, DMDB_ERR_ARG, e.what());
+  }
+  return check_device_errors(h);
+}
+
+int dmdb_get_state(dmdb_handle* h, int replica, double* sv, int32_t* bptnr, int32_t* identity, int32_t* extra_repuls,
+                   double* t, double* tfalse, int64_t* coll);
+
+int dmdb_set_temperature(dmdb_handle* h, int replica, double tstar) {
+  if (!h || !(tstar > 0)) return fail(h, DMDB_ERR_ARG, "bad argument");
+  const int r0 = replica < 0 ? 0 : replica, r1 = replica < 0 ? h->d.n_replicas : replica + 1;
+  if (replica >= 0) {
+    int rc = check_replica(h, replica, true);
+    if (rc) return rc;
+  }
+  DMDB_TRY(h, {
+    // what a new `./dmd < temp_0xx` run does: true positions -> restart files -> start-up path
+    be::run_op(h->d, dmd::OP_SYNC_POS, r0, r1 - r0, 0, nullptr, nullptr, &h->last_ms, &h->last_launches);
+    const int N = h->model.sys.N;
+    std::vector<double> sv((size_t)N * 6);
+    std::vector<int32_t> bp(N);
+    for (int r = r0; r < r1; r++) {
+      int rc = dmdb_get_state(h, r, sv.data(), bp.data(), nullptr, nullptr, nullptr, nullptr, nullptr);
+      if (rc) return rc;
+      h->tstar[r] = tstar;
+      upload_replica(h, r, sv.data(), bp.data());
+    }
+    be::run_op(h->d, dmd::OP_START, r0, r1 - r0, 0, nullptr, nullptr, &h->last_ms, &h->last_launches);
+  })
+  return check_device_errors(h);
+}
+
+int dmdb_nbor(dmdb_handle* h) {
+  int rc = all_loaded(h);
+  if (rc) return rc;
+  DMDB_TRY(h, be::run_op(h->d, dmd::OP_NBOR, 0, h->d.n_replicas, 0, nullptr, nullptr, &h->last_ms, &h->last_launches);)
+  return check_device_errors(h);
+}
+
+int dmdb_predict_all(dmdb_handle* h) {
+  int rc = all_loaded(h);
+  if (rc) return rc;
+  DMDB_TRY(h, be::run_op(h->d, dmd::OP_PREDICT_ALL, 0, h->d.n_replicas, 0, nullptr, nullptr, &h->last_ms,
+                         &h->last_launches);)
+  return check_device_errors(h);
+}
+
+int dmdb_get_replica_stats(dmdb_handle* h, int replica, dmdb_stats* s);
+
+int dmdb_run(dmdb_handle* h, int64_t n_events, dmdb_stats* stats) {
+  int rc = all_loaded(h);
+  if (rc) return rc;
+  if (n_events < 0) return fail(h, DMDB_ERR_ARG, "n_events must be >= 0");
+  DMDB_TRY(h, be::run_op(h->d, dmd::OP_RUN, 0, h->d.n_replicas, n_events, nullptr, nullptr, &h->last_ms,
+                         &h->last_launches);)
+  rc = check_device_errors(h);
+  if (rc) return rc;
+  if (stats) return dmdb_get_replica_stats(h, -1, stats);
+  return DMDB_OK;
+}
+
+int dmdb_sync_positions(dmdb_handle* h) {
+  int rc = all_loaded(h);
+  if (rc) return rc;
+  DMDB_TRY(h, be::run_op(h->d, dmd::OP_SYNC_POS, 0, h->d.n_replicas, 0, nullptr, nullptr, &h->last_ms,
+                         &h->last_launches);)
+  return DMDB_OK;
+}
+
+int dmdb_get_cells(dmdb_handle* h, int replica, int32_t* cell_of_bead) {
+  int rc = check_replica(h, replica, true);
+  if (rc) return rc;
+  const size_t N = (size_t)h->model.sys.N;
+  DMDB_TRY(h, be::d2h(cell_of_bead, h->d.cellof + (size_t)replica * N, N * 4);)
+  return DMDB_OK;
+}
+
+int dmdb_get_nbors(dmdb_handle* h, int replica, int down, int32_t* offsets, int32_t* nb) {
+  int rc = check_replica(h, replica, true);
+  if (rc) return rc;
+  const dmd::SysConst& s = h->model.sys;
+  const size_t N = (size_t)s.N, cap = (size_t)s.cap;
+  DMDB_TRY(h, {
+    std::vector<uint16_t> cnt(N);
+    be::d2h(cnt.data(), (down ? h->d.ndn : h->d.nup) + (size_t)replica * N, N * 2);
+    std::vector<uint32_t> lst;
+    if (nb) {
+      lst.resize(N * cap);
+      be::d2h(lst.data(), (down ? h->d.dn : h->d.up) + (size_t)replica * N * cap, N * cap * 4);
+    }
+    int n = 0;
+    for (size_t i = 0; i < N; i++) {
+      offsets[i] = n;
+      if (nb) {
+        for (int k = 0; k < cnt[i]; k++) nb[n + k] = (int32_t)(lst[i * cap + k] & dmd::NB_MASK) + 1;
+        std::sort(nb + n, nb + n + cnt[i]);
+      }
+      n += cnt[i];
+    }
+    offsets[N] = n;
+  })
+  return DMDB_OK;
+}
+
+int dmdb_get_calendar(dmdb_handle* h, int replica, double* tim, int32_t* nptnr, int32_t* coltype) {
+  int rc = check_replica(h, replica, true);
+  if (rc) return rc;
+  const size_t N = (size_t)h->model.sys.N;
+  DMDB_TRY(h, {
+    std::vector<int8_t> ct(N + 3);
+    be::d2h(tim, h->d.tim + (size_t)replica * h->d.tim_stride, (N + 3) * 8);
+    be::d2h(nptnr, h->d.nptnr + (size_t)replica * (N + 3), (N + 3) * 4);
+    be::d2h(ct.data(), h->d.ctype + (size_t)replica * (N + 3), N + 3);
+    for (size_t k = 0; k < N + 3; k++) {
+      coltype[k] = ct[k];
+      if (nptnr[k] >= 0) nptnr[k] += 1;  // 1-based partner; -1 none, -2 pseudo-event (main.F90:231-234)
+    }
+  })
+  return DMDB_OK;
+}
+
+int dmdb_get_state(dmdb_handle* h, int replica, double* sv, int32_t* bptnr, int32_t* identity, int32_t* extra_repuls,
+                   double* t, double* tfalse, int64_t* coll) {
+  int rc = check_replica(h, replica, true);
+  if (rc) return rc;
+  const size_t N = (size_t)h->model.sys.N;
+  DMDB_TRY(h, {
+    std::vector<dmd::BeadRec> rec(N);
+    be::d2h(rec.data(), h->d.rec + (size_t)replica * N, N * sizeof(dmd::BeadRec));
+    std::vector<int32_t> er34;
+    if (extra_repuls) {
+      er34.resize(2 * N);
+      be::d2h(er34.data(), h->d.er34 + (size_t)replica * 2 * N, 2 * N * 4);
+    }
+    for (size_t k = 0; k < N; k++) {
+      const dmd::BeadRec& b = rec[k];
+      if (sv) {
+        double* o = sv + 6 * k;
+        o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.vx; o[4] = b.vy; o[5] = b.vz;
+      }
+      if (bptnr) bptnr[k] = b.bptnr + 1;
+      if (identity) identity[k] = b.ident;
+      if (extra_repuls) {
+        extra_repuls[0 * N + k] = b.er1 + 1;
+        extra_repuls[1 * N + k] = b.er2 + 1;
+        extra_repuls[2 * N + k] = er34[2 * k] + 1;
+        extra_repuls[3 * N + k] = er34[2 * k + 1] + 1;
+      }
+    }
+    if (t || tfalse || coll) {
+      dmd::RepScalars sc;
+      be::d2h(&sc, h->d.scal + replica, sizeof(sc));
+      if (t) *t = sc.t;
+      if (tfalse) *tfalse = sc.tfalse;
+      if (coll) *coll = sc.coll;
+    }
+  })
+  return DMDB_OK;
+}
+
+int dmdb_get_evcode(dmdb_handle* h, int replica, int n_pairs, const int32_t* i, const int32_t* j, int32_t* code) {
+  int rc = check_replica(h, replica, true);
+  if (rc) return rc;
+  if (n_pairs <= 0) return DMDB_OK;
+  const int N = h->model.sys.N;
+  for (int k = 0; k < n_pairs; k++)
+    if (i[k] < 1 || i[k] > N || j[k] < 1 || j[k] > N || i[k] == j[k]) return fail(h, DMDB_ERR_ARG, "bad bead pair");
+  DMDB_TRY(h, {
+    if ((size_t)n_pairs > h->pair_cap) {
+      if (h->pair_buf) be::release(h->pair_buf);
+      h->pair_buf = (int32_t*)be::alloc((size_t)n_pairs * 3 * 4);
+      h->pair_cap = (size_t)n_pairs;
+    }
+    be::h2d(h->pair_buf, i, (size_t)n_pairs * 4);
+    be::h2d(h->pair_buf + n_pairs, j, (size_t)n_pairs * 4);
+    be::run_op(h->d, dmd::OP_EVCODE, replica, 1, n_pairs, h->pair_buf, nullptr, &h->last_ms, &h->last_launches);
+    be::d2h(code, h->pair_buf + 2 * (size_t)n_pairs, (size_t)n_pairs * 4);
+  })
+  return DMDB_OK;
+}
+
+int dmdb_energy_of(dmdb_handle* h, int replica, dmdb_energy* e) {
+  int rc = check_replica(h, replica, true);
+  if (rc) return rc;
+  DMDB_TRY(h, {
+    be::run_op(h->d, dmd::OP_ENERGY, replica, 1, 0, nullptr, h->eout, &h->last_ms, &h->last_launches);
+    dmd::OutRec o;
+    be::d2h(&o, h->eout + replica, sizeof(o));
+    e->ered = o.ered; e->tred = o.tred; e->sumvel = o.sumvel; e->ehh_ii = o.ehh_ii; e->ehh_ij = o.ehh_ij;
+    e->hb_alpha = o.hb_alpha; e->hb_ii = o.hb_ii; e->hb_ij = o.hb_ij; e->reserved = 0;
+  })
+  return DMDB_OK;
+}
+
+int dmdb_potential_energies(dmdb_handle* h, double* epot, double* tstar) {
+  int rc = all_loaded(h);
+  if (rc) return rc;
+  const int R = h->d.n_replicas;
+  DMDB_TRY(h, {
+    be::run_op(h->d, dmd::OP_ENERGY, 0, R, 0, nullptr, h->eout, &h->last_ms, &h->last_launches);
+    std::vector<dmd::OutRec> o(R);
+    be::d2h(o.data(), h->eout, sizeof(dmd::OutRec) * R);
+    for (int r = 0; r < R; r++) {
+      if (epot) epot[r] = o[r].ered - 0.5 * o[r].sumvel;  // e_int of main.F90:358
+      if (tstar) tstar[r] = h->tstar[r];
+    }
+  })
+  return DMDB_OK;
+}
+
+int dmdb_get_event_log(dmdb_handle* h, int replica, int64_t first, int64_t n, dmdb_event* out, int64_t* n_out) {
+  int rc = check_replica(h, replica, true);
+  if (rc) return rc;
+  static_assert(sizeof(dmdb_event) == sizeof(dmd::EventLogRec), "event record layout");
+  DMDB_TRY(h, {
+    dmd::RepScalars sc;
+    be::d2h(&sc, h->d.scal + replica, sizeof(sc));
+    int64_t avail = sc.n_log, m = 0;
+    if (first < avail) {
+      m = std::min<int64_t>(n, avail - first);
+      be::d2h(out, h->d.log + (size_t)replica * std::max(h->model.sys.log_cap, 1) + first, (size_t)m * sizeof(dmdb_event));
+    }
+    if (n_out) *n_out = m;
+  })
+  return DMDB_OK;
+}
+
+int dmdb_get_replica_stats(dmdb_handle* h, int replica, dmdb_stats* s) {
+  if (!h || !s) return DMDB_ERR_ARG;
+  if (replica >= 0) {
+    int rc = check_replica(h, replica, false);
+    if (rc) return rc;
+  }
+  DMDB_TRY(h, {
+    const int R = h->d.n_replicas;
+    std::vector<dmd::RepScalars> sc(R);
+    be::d2h(sc.data(), h->d.scal, sizeof(dmd::RepScalars) * R);
+    std::memset(s, 0, sizeof(*s));
+    for (int r = (replica < 0 ? 0 : replica); r < (replica < 0 ? R : replica + 1); r++) {
+      s->events += sc[r].coll;
+      for (int k = 0; k < 32; k++) {
+        s->nevents[k] += sc[r].nevents[k];
+        s->pair_events += sc[r].nevents[k];
+      }
+      s->ghosts += sc[r].numghosts;
+      s->updates += sc[r].nupdates - sc[r].nforcedupdate;
+      s->forced_updates += sc[r].nforcedupdate;
+      s->pair_predictions += sc[r].n_pair_pred;
+      s->nbr_visits += sc[r].n_nbr_visits;
+    }
+    s->device_ms = h->last_ms;
+    s->kernel_launches = h->last_launches;
+  })
+  return DMDB_OK;
+}
+
+}  // extern "C"

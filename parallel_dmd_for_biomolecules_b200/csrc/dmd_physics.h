@@ -1,0 +1,399 @@
+// dmd_physics.h -- scalar fp64 physics of the PRIME20 DMD hot path, written for the device (one lane = one
+// pair).  Every function names the reference routine it replaces (paths relative to
+// /root/reference/parallel-dmd-PRIME20/code).  Arithmetic contract (DESIGN.md "fp64 discipline"): IEEE fp64,
+// operations in the order the Fortran writes them, NO FMA contraction (nvcc -fmad=false), dnint == round().
+#pragma once
+#include "dmd_types.h"
+#include "dmd_warp.h"
+
+namespace dmd {
+
+constexpr double LTSTEP = 1e-10;   // def.h:1
+constexpr double SMDIST = 5e-12;   // def.h:2
+constexpr double T_NONE = 1000000000.0;  // events.f:28
+
+struct Ctx {                 // read-only context of one warp
+  const SysConst* sys;       // global memory (L2-resident, tiny)
+  const PairTables* tab;     // shared-memory copy of the 28x28 tables
+  const uint32_t* meta;
+  const int32_t* chain;
+};
+
+DMD_DEV int tix(int idi, int idj) { return (idi - 1) * 28 + (idj - 1); }
+
+// minimum-image pair geometry at the current false time (core.f:14-23 and every other predictor)
+struct Geom {
+  double vx, vy, vz, rx, ry, rz, bij;
+};
+DMD_DEV Geom pair_geom(const BeadRec& a, const BeadRec& b, double tfalse) {
+  Geom g;
+  g.vx = a.vx - b.vx;
+  g.vy = a.vy - b.vy;
+  g.vz = a.vz - b.vz;
+  g.rx = a.x - b.x + g.vx * tfalse;
+  g.ry = a.y - b.y + g.vy * tfalse;
+  g.rz = a.z - b.z + g.vz * tfalse;
+  g.rx = g.rx - dmd_round(g.rx);
+  g.ry = g.ry - dmd_round(g.ry);
+  g.rz = g.rz - dmd_round(g.rz);
+  g.bij = g.rx * g.vx + g.ry * g.vy + g.rz * g.vz;
+  return g;
+}
+
+// bond-length window of bond.f:30-41 / :80-91 for event classes 4-12; `mi` = topology word of the
+// lower-index (backbone) bead.
+DMD_DEV void bond_limits(const Ctx& c, int code, uint32_t mi, double& blmin, double& blmax) {
+  if (code >= 10) {
+    int r = (meta_sp(mi) ? c.sys->chnln[0] : 0) + meta_res(mi) - 1;
+    blmin = c.sys->blmin_sc[code - 10][r];
+    blmax = c.sys->blmax_sc[code - 10][r];
+  } else {
+    blmin = c.sys->ev_param2[code];
+    blmax = c.sys->ev_param3[code];
+  }
+}
+
+// hard-core diameter^2 of core.f:27-31 / eventdyn.f:70-74 / checkover.f:38-42
+DMD_DEV double core_sigsq(const Ctx& c, int code, int idi, int idj) {
+  double f = c.sys->ev_param1[code];
+  double sigsq = c.tab->sigma_sq[tix(idi, idj)] * (f * f);
+  if (code >= 22 && code <= 26) {
+    int k = idi > idj ? idi : idj;
+    double q = c.sys->sqz610[(code - 22) * 29 + k];
+    sigsq = sigsq * (q * q);
+  }
+  return sigsq;
+}
+
+// One pair-time prediction = the dispatch of events.f:30-48 + core.f / bond.f / sqwel.f / nc_sqwel.f /
+// sqshlder.f.  `a` is the lower-index bead (event owner), `bonded` = (bptnr(a) == b).  Leaves tij/type
+// untouched when the pair has no event (the Fortran leaves tij at its 1e9 preset).
+DMD_DEV void pair_time(const Ctx& c, int code, const BeadRec& a, const BeadRec& b, uint32_t meta_a, bool bonded,
+                       double tfalse, double& tij, int& type) {
+  const Geom g = pair_geom(a, b, tfalse);
+  const double bij = g.bij;
+  const double rijsq = g.rx * g.rx + g.ry * g.ry + g.rz * g.rz;
+  const double vijsq = g.vx * g.vx + g.vy * g.vy + g.vz * g.vz;
+  const int idi = a.ident, idj = b.ident;
+  if (code <= 3 || (code >= 17 && code <= 26)) {  // core.f:14-40
+    if (bij < 0.0) {
+      double sigsq = core_sigsq(c, code, idi, idj);
+      double discr = bij * bij - vijsq * (rijsq - sigsq);
+      if (discr > 0.0) {
+        tij = (-bij - dmd_sqrt(discr)) / vijsq;
+        type = 1;
+      }
+    }
+  } else if (code <= 12) {  // bond.f:27-126
+    double blmin, blmax;
+    bond_limits(c, code, meta_a, blmin, blmax);
+    if (bij < 0.0) {
+      double discr1 = bij * bij - vijsq * (rijsq - blmin * blmin);
+      if (discr1 > 0.0) {
+        tij = (-bij - dmd_sqrt(discr1)) / vijsq;
+        type = 2;
+      } else {
+        double discr2 = bij * bij - vijsq * (rijsq - blmax * blmax);
+        if (discr2 > 0.0) {
+          tij = (-bij + dmd_sqrt(discr2)) / vijsq;
+          type = 3;
+        }
+      }
+    } else {
+      double discr2 = bij * bij - vijsq * (rijsq - blmax * blmax);
+      if (discr2 > 0.0) {
+        tij = -(rijsq - blmax * blmax) / (dmd_sqrt(discr2) + bij);
+        type = 3;
+      }
+    }
+  } else if (code == 16) {  // sqwel.f:15-64
+    double diff = rijsq - c.tab->welldia_sq[tix(idi, idj)];
+    if (bij < 0.0) {
+      if (diff < 0.0) {
+        double corediscr = bij * bij - vijsq * (rijsq - c.tab->sigma_sq[tix(idi, idj)]);
+        if (corediscr > 0.0) {
+          tij = (-bij - dmd_sqrt(corediscr)) / vijsq;
+          type = 1;
+        } else {
+          double welldiscr = bij * bij - vijsq * diff;
+          tij = (-bij + dmd_sqrt(welldiscr)) / vijsq;
+          type = 8;
+        }
+      } else {
+        double welldiscr = bij * bij - vijsq * diff;
+        if (welldiscr > 0.0) {
+          tij = (-bij - dmd_sqrt(welldiscr)) / vijsq;
+          type = 4;
+        }
+      }
+    } else if (diff < 0.0) {
+      double welldiscr = bij * bij - vijsq * diff;
+      tij = (-bij + dmd_sqrt(welldiscr)) / vijsq;
+      type = 8;
+    }
+  } else if (code == 15) {  // nc_sqwel.f:19-122
+    double diff = rijsq - c.tab->welldia_sq[tix(idi, idj)];
+    if (idi + idj == 5) {
+      if (bij < 0.0) {
+        if (diff < 0.0) {
+          double corediscr = bij * bij - vijsq * (rijsq - c.tab->sigma_sq[tix(idi, idj)]);
+          if (corediscr > 0.0) {
+            tij = (-bij - dmd_sqrt(corediscr)) / vijsq;
+            type = 1;
+          } else {
+            double welldiscr = bij * bij - vijsq * diff;
+            tij = (-bij + dmd_sqrt(welldiscr)) / vijsq;
+            type = 16;
+          }
+        } else {
+          double welldiscr = bij * bij - vijsq * diff;
+          if (welldiscr > 0.0) {
+            tij = (-bij - dmd_sqrt(welldiscr)) / vijsq;
+            type = 7;
+          }
+        }
+      } else if (diff < 0.0) {
+        double welldiscr = bij * bij - vijsq * diff;
+        tij = (-bij + dmd_sqrt(welldiscr)) / vijsq;
+        type = 16;
+      }
+    } else if (bonded) {
+      if (bij < 0.0) {
+        double f = c.sys->ev_param1[15];
+        double fac_sigsq = c.tab->sigma_sq[tix(idi, idj)] * f * f;
+        double fac_cored = bij * bij - vijsq * (rijsq - fac_sigsq);
+        if (fac_cored > 0.0) {
+          tij = (-bij - dmd_sqrt(fac_cored)) / vijsq;
+          type = 1;
+        } else {
+          double welldiscr = bij * bij - vijsq * diff;
+          tij = (-bij + dmd_sqrt(welldiscr)) / vijsq;
+          type = 8;
+        }
+      } else {
+        double welldiscr = bij * bij - vijsq * diff;
+        tij = (-bij + dmd_sqrt(welldiscr)) / vijsq;
+        type = 8;
+      }
+    } else if (bij < 0.0) {
+      double welldiscr = bij * bij - vijsq * diff;
+      if (welldiscr > 0.0) {
+        tij = (-bij - dmd_sqrt(welldiscr)) / vijsq;
+        type = 9;
+      }
+    }
+  } else {  // code >= 40: sqshlder.f:15-63
+    double diff = rijsq - c.tab->shlddia_sq[tix(idi, idj)];
+    if (bij < 0.0) {
+      if (diff < 0.0) {
+        double corediscr = bij * bij - vijsq * (rijsq - c.tab->sigma_sq[tix(idi, idj)]);
+        if (corediscr > 0.0) {
+          tij = (-bij - dmd_sqrt(corediscr)) / vijsq;
+          type = 1;
+        } else {
+          double shlddiscr = bij * bij - vijsq * diff;
+          tij = (-bij + dmd_sqrt(shlddiscr)) / vijsq;
+          type = 10;
+        }
+      } else {
+        double shlddiscr = bij * bij - vijsq * diff;
+        if (shlddiscr > 0.0) {
+          tij = (-bij - dmd_sqrt(shlddiscr)) / vijsq;
+          type = 12;
+        }
+      }
+    } else if (diff < 0.0) {
+      double shlddiscr = bij * bij - vijsq * diff;
+      tij = (-bij + dmd_sqrt(shlddiscr)) / vijsq;
+      type = 10;
+    }
+  }
+}
+
+// distance between two beads at the current false time (repuls_check.f:32-42)
+DMD_DEV double pair_dist(const BeadRec& a, const BeadRec& b, double tfalse) {
+  Geom g = pair_geom(a, b, tfalse);
+  double d = g.rx * g.rx + g.ry * g.ry + g.rz * g.rz;
+  return dmd_sqrt(d);
+}
+
+// eventdyn.f:18-381.  `a` owner (lower index), `b` partner; ct = resolved coltype (< 14).  Returns the
+// executed type (20..27 or the unchanged 1/2/3).  Updates positions (bump + rewind) and velocities.
+DMD_DEV int event_dynamics(const Ctx& c, int ct, int code, BeadRec& a, BeadRec& b, uint32_t meta_a, bool bonded,
+                           double tfalse) {
+  const Geom g = pair_geom(a, b, tfalse);
+  const double rxij = g.rx, ryij = g.ry, rzij = g.rz, bij = g.bij;
+  const int idi = a.ident, idj = b.ident;
+  const double bmi = c.sys->bmass[idi], bmj = c.sys->bmass[idj];
+  const double rmass = 2 * bmi * bmj / (bmi + bmj);
+  double ratio = 0.0, bumpdist = 0.0, sgn = 0.0;  // sgn +1: a += bump*r, b -= ; -1: the opposite
+  if (ct == 2 || ct == 3) {
+    double blmin, blmax;
+    bond_limits(c, code, meta_a, blmin, blmax);
+    ratio = ct == 2 ? rmass * bij / (blmin * blmin) : rmass * bij / (blmax * blmax);
+  } else if (ct == 1) {
+    double sigsq;
+    if (code == 15) {
+      double f = c.sys->ev_param1[15];
+      sigsq = bonded ? c.tab->sigma_sq[tix(idi, idj)] * (f * f) : c.tab->sigma_sq[tix(idi, idj)];
+    } else {
+      sigsq = core_sigsq(c, code, idi, idj);
+    }
+    ratio = rmass * bij / sigsq;
+  } else if (ct == 4 || ct == 8 || ct == 9) {
+    double wellsq = c.tab->welldia_sq[tix(idi, idj)];
+    double epsave = c.tab->ep_sqrt[tix(idi, idj)];
+    double del_pe = 4.0 * wellsq * epsave / rmass;
+    bumpdist = SMDIST * dmd_sqrt(wellsq);
+    if (ct == 4) {
+      if (bij * bij + del_pe > 0.0) {
+        ratio = rmass * (dmd_sqrt((4.0 * wellsq * epsave / rmass) + bij * bij) + bij) / (2.0 * wellsq);
+        ct = 20;
+        sgn = -1.0;
+      } else {
+        ratio = rmass * bij / wellsq;
+        ct = 22;
+        sgn = 1.0;
+      }
+    } else if (ct == 8) {
+      if (bij * bij > del_pe) {
+        ratio = rmass * (-dmd_sqrt(-del_pe + bij * bij) + bij) / (2.0 * wellsq);
+        ct = 21;
+        sgn = 1.0;
+      } else {
+        ratio = rmass * bij / wellsq;
+        ct = 22;
+        sgn = -1.0;
+      }
+    } else {
+      ratio = rmass * bij / wellsq;
+      ct = 23;
+      sgn = 1.0;
+    }
+  } else if (ct == 5 || ct == 6 || ct == 13) {
+    double wellsq = c.tab->shlddia_sq[tix(idi, idj)];
+    double epsave = -c.sys->eps1;
+    double del_pe = 4.0 * wellsq * epsave / rmass;
+    bumpdist = SMDIST * dmd_sqrt(wellsq);
+    if (ct == 5) {
+      ratio = rmass * (-dmd_sqrt(-del_pe + bij * bij) + bij) / (2.0 * wellsq);
+      ct = 24;
+      sgn = 1.0;
+    } else if (ct == 6) {
+      if (bij * bij > -del_pe) {
+        ratio = rmass * (dmd_sqrt(del_pe + bij * bij) + bij) / (2.0 * wellsq);
+        ct = 25;
+        sgn = -1.0;
+      } else {
+        ratio = rmass * bij / wellsq;
+        ct = 26;
+        sgn = 1.0;
+      }
+    } else {
+      ratio = rmass * bij / wellsq;
+      ct = 27;
+      sgn = 1.0;
+    }
+  }
+  if (sgn != 0.0) {  // the 5e-12*d "bump" off the discontinuity, eventdyn.f:85-91 etc.
+    a.x = a.x + sgn * (bumpdist * rxij);
+    a.y = a.y + sgn * (bumpdist * ryij);
+    a.z = a.z + sgn * (bumpdist * rzij);
+    b.x = b.x - sgn * (bumpdist * rxij);
+    b.y = b.y - sgn * (bumpdist * ryij);
+    b.z = b.z - sgn * (bumpdist * rzij);
+  }
+  const double delvx = ratio * rxij, delvy = ratio * ryij, delvz = ratio * rzij;  // eventdyn.f:366-381
+  a.vx = a.vx - delvx / bmi;
+  b.vx = b.vx + delvx / bmj;
+  a.vy = a.vy - delvy / bmi;
+  b.vy = b.vy + delvy / bmj;
+  a.vz = a.vz - delvz / bmi;
+  b.vz = b.vz + delvz / bmj;
+  a.x = a.x + delvx * tfalse / bmi;
+  a.y = a.y + delvy * tfalse / bmi;
+  a.z = a.z + delvz * tfalse / bmi;
+  b.x = b.x - delvx * tfalse / bmj;
+  b.y = b.y - delvy * tfalse / bmj;
+  b.z = b.z - delvz * tfalse / bmj;
+  return ct;
+}
+
+// bumped.f:12-43
+DMD_DEV void bump_off(const Ctx& c, int code, BeadRec& a, BeadRec& b, double tfalse) {
+  const Geom g = pair_geom(a, b, tfalse);
+  double dsq = code >= 40 ? c.tab->shlddia_sq[tix(a.ident, b.ident)] : c.tab->welldia_sq[tix(a.ident, b.ident)];
+  double bumpdist = SMDIST * dmd_sqrt(dsq);
+  double sgn = g.bij < 0.0 ? -1.0 : 1.0;
+  a.x = a.x + sgn * (bumpdist * g.rx);
+  a.y = a.y + sgn * (bumpdist * g.ry);
+  a.z = a.z + sgn * (bumpdist * g.rz);
+  b.x = b.x - sgn * (bumpdist * g.rx);
+  b.y = b.y - sgn * (bumpdist * g.ry);
+  b.z = b.z - sgn * (bumpdist * g.rz);
+}
+
+// counter RNG replacing Intel IFPORT drandm (main.F90:173,412,998,1009-1010,1041,1510): splitmix64 of
+// (seed + n*golden) -> 53-bit uniform in [0,1).  Shared bit-for-bit with the oracle.
+DMD_DEV double rng_uniform(uint64_t seed, uint64_t& ctr) {
+  ctr += 1;
+  uint64_t z = seed + ctr * 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z = z ^ (z >> 31);
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// natural log for the ghost thermostat (main.F90:1016,1044): the fdlibm e_log.c algorithm with plain
+// (unfused) fp64 operations so host oracle and device agree bit for bit.  x must be positive and finite.
+DMD_DEV double dmd_log(double x) {
+  const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
+               Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+               Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+               Lg7 = 1.479819860511658591e-01;
+  int hx = dmd_hi(x);
+  unsigned lx = dmd_lo(x);
+  int k = 0;
+  if (hx < 0x00100000) {
+    x *= 1.80143985094819840000e+16;
+    k -= 54;
+    hx = dmd_hi(x);
+    lx = dmd_lo(x);
+  }
+  k += (hx >> 20) - 1023;
+  hx &= 0x000fffff;
+  int i = (hx + 0x95f64) & 0x100000;
+  x = dmd_hi_lo(hx | (i ^ 0x3ff00000), lx);
+  k += (i >> 20);
+  double f = x - 1.0, dk;
+  if ((0x000fffff & (2 + hx)) < 3) {
+    if (f == 0.0) {
+      if (k == 0) return 0.0;
+      dk = (double)k;
+      return dk * ln2_hi + dk * ln2_lo;
+    }
+    double R = f * f * (0.5 - 0.33333333333333333 * f);
+    if (k == 0) return f - R;
+    dk = (double)k;
+    return dk * ln2_hi - ((R - dk * ln2_lo) - f);
+  }
+  double s = f / (2.0 + f);
+  dk = (double)k;
+  double z = s * s;
+  i = hx - 0x6147a;
+  double w = z * z;
+  int j = 0x6b851 - hx;
+  double t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+  double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+  i |= j;
+  double R = t2 + t1;
+  if (i > 0) {
+    double hfsq = 0.5 * f * f;
+    if (k == 0) return f - (hfsq - s * (hfsq + R));
+    return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
+  }
+  if (k == 0) return f - s * (f - R);
+  return dk * ln2_hi - ((s * (f - R) - dk * ln2_lo) - f);
+}
+
+}  // namespace dmd

@@ -1,0 +1,151 @@
+// dmd_types.h -- data layout of the B200 engine (host + device).
+//
+// Design: ONE WARP OWNS ONE REPLICA (an independent PRIME20 trajectory).  All per-replica state lives in
+// HBM in structure-of-arrays blocks with a fixed replica stride; a warp streams its replica's data with
+// coalesced 32-wide accesses (calendar groups, position advance) and 64-byte bead-record gathers (pair
+// prediction).  Nothing is shared between warps, so the event loop needs no atomics and no block barriers.
+//
+// Reference state this replaces: module `global`, code/header.f:14-63 (sv, tim, nptnr, coltype, identity,
+// bptnr, extra_repuls, ev_code, nb/dnnab, bin/tlinks, cell/clinks, scalars).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define DMD_HD __host__ __device__ __forceinline__
+#else
+#define DMD_HD inline
+#endif
+
+namespace dmd {
+
+// ---- one bead, 64 bytes, 64-byte aligned: a partner gather is exactly two 32-byte sectors ----------------
+// sv(1:6,k) of header.f:42 + identity (header.f:22) + bptnr + the bead's two auxiliary partners
+// extra_repuls(k,1:2) (header.f:20) + the ev_code overlay (40/50/1) of those two pairs as seen from row k.
+struct alignas(64) BeadRec {
+  double x, y, z, vx, vy, vz;
+  int32_t bptnr;   // 0-based partner or -1
+  int32_t er1;     // extra_repuls(k,1), 0-based or -1
+  int32_t er2;     // extra_repuls(k,2)
+  uint8_t ident;   // identity 1..28 (changes by +-4 on H-bond formation, main.F90:1643)
+  uint8_t ov1;     // ev_code(k, er1): 1 (off), 40 or 50
+  uint8_t ov2;     // ev_code(k, er2)
+  uint8_t pad;
+};
+static_assert(sizeof(BeadRec) == 64, "BeadRec must be 64 bytes");
+
+// per-bead static topology word (shared by all replicas): what make_code.f derives its N x N matrix from
+//   bits 0-1 class (0 Ca, 1 N, 2 C, 3 R) | 2-11 residue index 1..L | 12 hp flag | 13-17 initial identity |
+//   18 species | 19 proline-exclusion flag for N beads (make_code.f:146-168) | 20-29 bead index local to chain
+DMD_HD uint32_t meta_pack(int cls, int res, int hp, int id0, int sp, int proex, int local) {
+  return (uint32_t)cls | ((uint32_t)res << 2) | ((uint32_t)hp << 12) | ((uint32_t)id0 << 13) | ((uint32_t)sp << 18) |
+         ((uint32_t)proex << 19) | ((uint32_t)local << 20);
+}
+DMD_HD int meta_cls(uint32_t m) { return m & 3; }
+DMD_HD int meta_res(uint32_t m) { return (m >> 2) & 1023; }
+DMD_HD int meta_hp(uint32_t m) { return (m >> 12) & 1; }
+DMD_HD int meta_id0(uint32_t m) { return (m >> 13) & 31; }
+DMD_HD int meta_sp(uint32_t m) { return (m >> 18) & 1; }
+DMD_HD int meta_proex(uint32_t m) { return (m >> 19) & 1; }
+DMD_HD int meta_local(uint32_t m) { return (m >> 20) & 1023; }
+
+// neighbour-list entry: static ev_code class in the top 5 bits, partner index in the low 27
+constexpr int NB_SHIFT = 27;
+constexpr uint32_t NB_MASK = (1u << NB_SHIFT) - 1;
+
+constexpr int MAX_RES = 512;   // residues over both species (bond-limit tables)
+
+// 28 x 28 pair tables of scale_down.f:37-67, index (id_i-1)*28 + (id_j-1); staged into shared memory
+struct PairTables {
+  double sigma_sq[784];
+  double welldia_sq[784];
+  double shlddia_sq[784];
+  double ep_sqrt[784];
+};
+
+// everything that is constant during a run and identical for all replicas
+struct SysConst {
+  int32_t N;                 // beads per replica
+  int32_t n_species, nop1;   // nop1 = beads of species 1
+  int32_t nch[2], chnln[2], numbeads[2];
+  int32_t n_wrap, num_cell, ncr;  // num_cell per dim incl. ghosts (main.F90:390), ncr = real cells per dim
+  int32_t canon, no_hbs;
+  int32_t cap;               // per-bead capacity of each neighbour list
+  int32_t ngroups;           // ceil((N+3)/32) calendar groups
+  int32_t log_cap, out_cap;
+  double ev_param1[51];      // make_code.f:18-39 (squeeze factors), index = ev_code
+  double ev_param2[51];      // blmin of codes 4-9 (make_code.f:49-57)
+  double ev_param3[51];      // blmax
+  double sqz610[5 * 29];     // inputinfo.f:382-389, [(code-22)*29 + identity]
+  double rlsq[51];           // nbor_setup.f:112-115
+  double bmass[29];          // inputinfo.f:395-404
+  double shder[4];           // scale_down.f:32-35
+  double eps1;               // epsilon(1)
+  double eps_hb;             // ep_sqrt(5,8), energy.f:74
+  double hdelr, width, half, sig_max_all, boxl_orig;
+  // per-residue side-chain bond limits, already multiplied out like bond.f:82-91:
+  // [kind 0:R-Ca(10) 1:R-N(11) 2:R-C(12)][species residue index: species 0 -> r-1, species 1 -> chnln[0]+r-1]
+  double blmin_sc[3][MAX_RES];
+  double blmax_sc[3][MAX_RES];
+};
+
+// per-replica scalars (main.F90 locals + module scalars header.f:47-48)
+struct alignas(128) RepScalars {
+  double t, tfalse, old_tfalse;
+  double setemp, interval, t_fact, interval_max, n_forced, avegtime;
+  int64_t coll;
+  uint64_t rng_seed, rng_ctr;
+  int64_t nevents[32];
+  int64_t numghosts, nupdates, nforcedupdate;
+  int64_t n_pair_pred, n_nbr_visits;
+  int32_t n_log, n_out;
+  int32_t error;        // 0 ok; see DMD_E_* below
+  int32_t error_info;
+  int32_t pad[4];
+};
+
+constexpr int DMD_E_NBR_CAP = 1;    // neighbour list capacity exceeded
+constexpr int DMD_E_CAL_EMPTY = 2;  // calendar has no finite entry
+constexpr int DMD_E_NEG_TIME = 3;   // tij < -1e-10 (events.f:59-73 debugging guard)
+constexpr int DMD_E_GRID = 4;       // bead outside the cell grid
+
+struct EventLogRec {  // == dmdb_event
+  double t;
+  int32_t i, j, type, evcode;
+};
+
+struct OutRec {  // one output pseudo-event (main.F90:1207-1210)
+  int64_t coll;
+  double t, ered, tred, sumvel, ehh_ii, ehh_ij;
+  int32_t hb_alpha, hb_ii, hb_ij, pad;
+};
+
+// device pointers; element (replica r, index k) of array A with per-replica length n is A[r*n + k]
+struct DevArrays {
+  // shared by all replicas
+  const SysConst* sys;
+  const PairTables* tables;
+  const uint32_t* meta;   // N
+  const int32_t* chain;   // N (global chain index)
+  // per replica
+  BeadRec* rec;           // N
+  double* tim;            // N+3 (padded to ngroups*32)
+  int32_t* nptnr;         // N+3, 0-based partner or -1
+  int8_t* ctype;          // N+3
+  int32_t* er34;          // 2N: extra_repuls(k,3), extra_repuls(k,4), 0-based or -1
+  uint32_t* up;           // N*cap
+  uint32_t* dn;           // N*cap
+  uint16_t* nup;          // N
+  uint16_t* ndn;          // N
+  double* oldr;           // 3N
+  int32_t* cellhead;      // ncr^3
+  int32_t* cnext;         // N
+  int32_t* cellof;        // N (reference cell id of cell_add.f:25, for parity read-back)
+  double* tmin1;          // ngroups
+  RepScalars* scal;       // 1
+  EventLogRec* log;       // log_cap
+  OutRec* out;            // out_cap
+  int32_t n_replicas;
+  int32_t tim_stride;     // ngroups*32
+};
+
+}  // namespace dmd

@@ -1,0 +1,113 @@
+// dmd_warp.h -- the 32-lane warp primitives the engine is written against.
+//
+// Device build (nvcc, sm_100a): real shuffles / ballots, DMD_W == 32.
+// DMD_HOST_TRACE build (g++, tests/host_trace only): a 1-lane "warp" (DMD_W == 1) so the SAME engine source
+// can be single-stepped on the CPU against the oracle to debug the event-loop logic without a GPU.  That
+// build is test scaffolding; it is never linked into libdmdb200.so and is not a fallback.
+#pragma once
+#include <stdint.h>
+
+#if defined(DMD_HOST_TRACE)
+#include <cmath>
+#include <cstring>
+#define DMD_DEV inline
+#define DMD_W 1
+namespace dmd {
+struct Warp {
+  static inline int lane() { return 0; }
+  static inline void sync() {}
+  static inline unsigned ballot(bool p) { return p ? 1u : 0u; }
+  static inline bool any(bool p) { return p; }
+  static inline int shfl(int v, int) { return v; }
+  static inline double shfl(double v, int) { return v; }
+  static inline int shfl_down(int v, int) { return v; }
+  static inline double shfl_down(double v, int) { return v; }
+  static inline int shfl_xor(int v, int) { return v; }
+  static inline double shfl_xor(double v, int) { return v; }
+  static inline long long shfl_xor(long long v, int) { return v; }
+};
+DMD_DEV int dmd_ffs(unsigned m) { return __builtin_ffs((int)m); }
+DMD_DEV int dmd_popc(unsigned m) { return __builtin_popcount(m); }
+DMD_DEV double dmd_sqrt(double x) { return std::sqrt(x); }
+DMD_DEV double dmd_round(double x) { return std::round(x); }
+DMD_DEV double dmd_hi_lo(int hi, unsigned lo) {
+  uint64_t b = ((uint64_t)(uint32_t)hi << 32) | lo;
+  double d;
+  std::memcpy(&d, &b, 8);
+  return d;
+}
+DMD_DEV int dmd_hi(double d) {
+  uint64_t b;
+  std::memcpy(&b, &d, 8);
+  return (int)(b >> 32);
+}
+DMD_DEV unsigned dmd_lo(double d) {
+  uint64_t b;
+  std::memcpy(&b, &d, 8);
+  return (unsigned)b;
+}
+}  // namespace dmd
+#else
+#define DMD_DEV __device__ __forceinline__
+#define DMD_W 32
+namespace dmd {
+struct Warp {
+  static __device__ __forceinline__ int lane() { return threadIdx.x & 31; }
+  static __device__ __forceinline__ void sync() { __syncwarp(); }
+  static __device__ __forceinline__ unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+  static __device__ __forceinline__ bool any(bool p) { return __any_sync(0xffffffffu, p); }
+  static __device__ __forceinline__ int shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+  static __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+  static __device__ __forceinline__ int shfl_xor(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+  static __device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+  static __device__ __forceinline__ long long shfl_xor(long long v, int m) {
+    return __shfl_xor_sync(0xffffffffu, v, m);
+  }
+};
+DMD_DEV int dmd_ffs(unsigned m) { return __ffs((int)m); }
+DMD_DEV int dmd_popc(unsigned m) { return __popc(m); }
+DMD_DEV double dmd_sqrt(double x) { return sqrt(x); }    // IEEE-exact fp64 sqrt on device
+DMD_DEV double dmd_round(double x) { return round(x); }  // round half away from zero == Fortran dnint
+DMD_DEV double dmd_hi_lo(int hi, unsigned lo) { return __hiloint2double(hi, (int)lo); }
+DMD_DEV int dmd_hi(double d) { return __double2hiint(d); }
+DMD_DEV unsigned dmd_lo(double d) { return (unsigned)__double2loint(d); }
+}  // namespace dmd
+#endif
+
+namespace dmd {
+
+// (value, key) lexicographic arg-min over the warp: smallest value, ties -> smallest key.  All lanes get it.
+DMD_DEV void warp_argmin(double& v, int& key) {
+#if DMD_W > 1
+#pragma unroll
+  for (int m = DMD_W / 2; m >= 1; m >>= 1) {
+    double ov = Warp::shfl_xor(v, m);
+    int ok = Warp::shfl_xor(key, m);
+    if (ov < v || (ov == v && ok < key)) {
+      v = ov;
+      key = ok;
+    }
+  }
+#endif
+}
+
+DMD_DEV double warp_max(double v) {
+#if DMD_W > 1
+#pragma unroll
+  for (int m = DMD_W / 2; m >= 1; m >>= 1) {
+    double ov = Warp::shfl_xor(v, m);
+    if (ov > v) v = ov;
+  }
+#endif
+  return v;
+}
+
+DMD_DEV int warp_sum(int v) {
+#if DMD_W > 1
+#pragma unroll
+  for (int m = DMD_W / 2; m >= 1; m >>= 1) v += Warp::shfl_xor(v, m);
+#endif
+  return v;
+}
+
+}  // namespace dmd
