@@ -117,7 +117,7 @@ int dmdb_create(const dmdb_params* p, const dmdb_topology* topo, const dmdb_tabl
     dmd::DevArrays& d = h->d;
     std::memset(&d, 0, sizeof(d));
     d.n_replicas = (int)R;
-    d.tim_stride = s.ngroups * 32;
+    d.cal_stride = s.ngroups * 32;
     dmd::SysConst* dsys = dalloc<dmd::SysConst>(h.get(), 1);
     be::h2d(dsys, &s, sizeof(s));
     d.sys = dsys;
@@ -131,9 +131,7 @@ int dmdb_create(const dmdb_params* p, const dmdb_topology* topo, const dmdb_tabl
     be::h2d(dchain, h->model.chain.data(), N * 4);
     d.chain = dchain;
     d.rec = dalloc<dmd::BeadRec>(h.get(), R * N);
-    d.tim = dalloc<double>(h.get(), R * d.tim_stride);
-    d.nptnr = dalloc<int32_t>(h.get(), R * (N + 3));
-    d.ctype = dalloc<int8_t>(h.get(), R * (N + 3));
+    d.cal = dalloc<dmd::CalEnt>(h.get(), R * d.cal_stride);
     d.er34 = dalloc<int32_t>(h.get(), R * 2 * N);
     d.up = dalloc<uint32_t>(h.get(), R * N * s.cap);
     d.dn = dalloc<uint32_t>(h.get(), R * N * s.cap);
@@ -180,14 +178,12 @@ static int upload_replica(dmdb_handle* h, int r, const double* sv, const int32_t
   const dmd::SysConst& s = h->model.sys;
   const size_t N = (size_t)s.N, rr = (size_t)r;
   dmd::HostReplicaInit init;
-  dmd::build_replica_init(h->model, sv, bptnr, h->tstar[r], h->model.params.seed + (uint64_t)r, h->d.tim_stride, init);
+  dmd::build_replica_init(h->model, sv, bptnr, h->tstar[r], h->model.params.seed + (uint64_t)r, h->d.cal_stride, init);
   dmd::DevArrays& d = h->d;
   be::h2d(d.rec + rr * N, init.rec.data(), N * sizeof(dmd::BeadRec));
   be::h2d(d.er34 + rr * 2 * N, init.er34.data(), 2 * N * 4);
   be::h2d(d.oldr + rr * 3 * N, init.oldr.data(), 3 * N * 8);
-  be::h2d(d.tim + rr * d.tim_stride, init.tim.data(), (size_t)d.tim_stride * 8);
-  be::h2d(d.nptnr + rr * (N + 3), init.nptnr.data(), (N + 3) * 4);
-  be::h2d(d.ctype + rr * (N + 3), init.ctype.data(), (N + 3));
+  be::h2d(d.cal + rr * d.cal_stride, init.cal.data(), (size_t)d.cal_stride * sizeof(dmd::CalEnt));
   be::h2d(d.scal + rr, &init.scal, sizeof(dmd::RepScalars));
   h->loaded[r] = 1;
   return 0;
@@ -313,13 +309,12 @@ int dmdb_get_calendar(dmdb_handle* h, int replica, double* tim, int32_t* nptnr, 
   if (rc) return rc;
   const size_t N = (size_t)h->model.sys.N;
   DMDB_TRY(h, {
-    std::vector<int8_t> ct(N + 3);
-    be::d2h(tim, h->d.tim + (size_t)replica * h->d.tim_stride, (N + 3) * 8);
-    be::d2h(nptnr, h->d.nptnr + (size_t)replica * (N + 3), (N + 3) * 4);
-    be::d2h(ct.data(), h->d.ctype + (size_t)replica * (N + 3), N + 3);
+    std::vector<dmd::CalEnt> cal(N + 3);
+    be::d2h(cal.data(), h->d.cal + (size_t)replica * h->d.cal_stride, (N + 3) * sizeof(dmd::CalEnt));
     for (size_t k = 0; k < N + 3; k++) {
-      coltype[k] = ct[k];
-      if (nptnr[k] >= 0) nptnr[k] += 1;  // 1-based partner; -1 none, -2 pseudo-event (main.F90:231-234)
+      tim[k] = cal[k].t;
+      coltype[k] = (int8_t)(cal[k].type & 0xff);
+      nptnr[k] = cal[k].ptnr >= 0 ? cal[k].ptnr + 1 : cal[k].ptnr;  // 1-based; -1 none, -2 pseudo (main.F90:231-234)
     }
   })
   return DMDB_OK;

@@ -35,6 +35,11 @@ __device__ __forceinline__ const PairTables* stage_tables(const DevArrays& d, Pa
   return smem;
 }
 
+__device__ __forceinline__ int32_t* warp_queue() {
+  __shared__ int32_t s_cq[WARPS_PER_CTA][CQ_CAP];
+  return s_cq[threadIdx.x >> 5];
+}
+
 __device__ __forceinline__ int replica_of_warp(int r0, int nrep) {
   int w = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
   return w < nrep ? r0 + w : -1;
@@ -46,7 +51,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_event_loop_kernel(DevA
   int rid = replica_of_warp(r0, nrep);
   if (rid < 0) return;
   Rep r;
-  rep_bind(r, d, tab, rid);
+  rep_bind(r, d, tab, warp_queue(), rid);
   if (r.error == 0) run_events(r, n_events);
   rep_save(r);
 }
@@ -57,11 +62,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_start_kernel(DevArrays
   int rid = replica_of_warp(r0, nrep);
   if (rid < 0) return;
   Rep r;
-  rep_bind(r, d, tab, rid);
+  rep_bind(r, d, tab, warp_queue(), rid);
   if (d.sys->canon) {  // main.F90:408-416
     double tgho = 0.0;
     while (tgho < 1e-18 || tgho == 1.0) tgho = rng_uniform(r.seed, r.ctr);
-    if (Warp::lane() == 0) r.tim[r.N] = -1.0 * dmd_log(tgho) * r.avegtime * .0000001;
+    if (Warp::lane() == 0) r.cal[r.N].t = -1.0 * dmd_log(tgho) * r.avegtime * .0000001;
   }
   nbor(r);
   predict_all(r);
@@ -74,7 +79,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_nbor_kernel(DevArrays 
   int rid = replica_of_warp(r0, nrep);
   if (rid < 0) return;
   Rep r;
-  rep_bind(r, d, tab, rid);
+  rep_bind(r, d, tab, warp_queue(), rid);
   nbor(r);
   rep_save(r);
 }
@@ -85,7 +90,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_predict_all_kernel(Dev
   int rid = replica_of_warp(r0, nrep);
   if (rid < 0) return;
   Rep r;
-  rep_bind(r, d, tab, rid);
+  rep_bind(r, d, tab, warp_queue(), rid);
   predict_all(r);
   rep_save(r);
 }
@@ -94,7 +99,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_sync_positions_kernel(
   int rid = replica_of_warp(r0, nrep);
   if (rid < 0) return;
   Rep r;
-  rep_bind(r, d, d.tables, rid);
+  rep_bind(r, d, d.tables, warp_queue(), rid);
   sync_positions(r);
 }
 
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_energy_kernel(DevArray
   int rid = replica_of_warp(r0, nrep);
   if (rid < 0) return;
   Rep r;
-  rep_bind(r, d, tab, rid);
+  rep_bind(r, d, tab, warp_queue(), rid);
   OutRec o;
   energy_of(r, o);
   if (Warp::lane() == 0) eout[rid] = o;

@@ -3,9 +3,12 @@
 // One warp runs the whole serial-semantics event loop of main.F90:484-1258 for its replica:
 //   pop_min        two-level min-reduction calendar (replaces add_tbin.f/del_tbin.f + main.F90:496-545)
 //   pair_event     resolution main.F90:1487-1634, eventdyn.f, bookkeeping main.F90:1638-1937
-//   partial_events partial_events.f:16-201 with lanes over the neighbour lists
-//   ghost/interval/output pseudo-events main.F90:997-1049, 1126-1187, 1191-1246
-//   cell_build/nbor_build/predict_all (cell_add.f, nbor.f, events.f) with one lane per bead
+//   partial_events partial_events.f:16-201: ONE pass per colliding bead, lanes over its up-list, aux slots
+//                  and down-list at once; cascaded full re-predictions go through the same pass
+//   ghost/interval/output pseudo-events main.F90:997-1049, 1126-1187, 1191-1246  (cold, out of line)
+//   cell_build/nbor_build/predict_all (cell_add.f, nbor.f, events.f) with one lane per bead (cold)
+// The hot loop is kept small (it must live in the instruction cache while 16+ warps per SM sit at different
+// program counters); everything rare is __noinline__ and takes the replica view by value.
 // Every loop is written for DMD_W lanes (32 on the device, 1 in the host trace build).
 #pragma once
 #include "dmd_physics.h"
@@ -13,18 +16,22 @@
 #include "dmd_types.h"
 #include "dmd_warp.h"
 
+#if defined(DMD_HOST_TRACE)
+#define DMD_COLD inline
+#else
+#define DMD_COLD __device__ __noinline__
+#endif
+
 namespace dmd {
 
 constexpr double T_PAD = 1e300;  // calendar padding entries
-constexpr int MAX_DIRTY = 12;
+constexpr int CQ_CAP = 160;      // cascade queue (<= one entry per down-list candidate of a pass)
 
 struct Rep {
   Ctx c;
   int N, cap, G;
   BeadRec* rec;
-  double* tim;
-  int32_t* nptnr;
-  int8_t* ctype;
+  CalEnt* cal;
   int32_t* er34;
   uint32_t *up, *dn;
   uint16_t *nup, *ndn;
@@ -34,17 +41,26 @@ struct Rep {
   RepScalars* sc;
   EventLogRec* log;
   OutRec* out;
+  int32_t* cq;  // cascade queue storage (shared memory on the device)
   // scalars cached in registers (identical in every lane)
   double t, tfalse, old_tfalse, setemp, interval, t_fact, interval_max, n_forced, avegtime;
   int64_t coll;
   uint64_t seed, ctr;
   int64_t n_pair_pred, n_nbr_visits;
   int32_t n_log, n_out, error, error_info;
-  int dirty[MAX_DIRTY];
-  int ndirty;
+  uint64_t dirty0, dirty1;  // calendar groups 0..127 whose minimum is stale
 };
 
-DMD_DEV void rep_bind(Rep& r, const DevArrays& d, const PairTables* tab, int rid) {
+DMD_DEV void rep_load_scalars(Rep& r) {
+  const RepScalars& q = *r.sc;
+  r.t = q.t; r.tfalse = q.tfalse; r.old_tfalse = q.old_tfalse; r.setemp = q.setemp; r.interval = q.interval;
+  r.t_fact = q.t_fact; r.interval_max = q.interval_max; r.n_forced = q.n_forced; r.avegtime = q.avegtime;
+  r.coll = q.coll; r.seed = q.rng_seed; r.ctr = q.rng_ctr;
+  r.n_pair_pred = q.n_pair_pred; r.n_nbr_visits = q.n_nbr_visits;
+  r.n_log = q.n_log; r.n_out = q.n_out; r.error = q.error; r.error_info = q.error_info;
+}
+
+DMD_DEV void rep_bind(Rep& r, const DevArrays& d, const PairTables* tab, int32_t* cq, int rid) {
   const SysConst* s = d.sys;
   r.c.sys = s;
   r.c.tab = tab;
@@ -56,9 +72,7 @@ DMD_DEV void rep_bind(Rep& r, const DevArrays& d, const PairTables* tab, int rid
   r.G = s->ngroups;
   const size_t rr = (size_t)rid;
   r.rec = d.rec + rr * N;
-  r.tim = d.tim + rr * d.tim_stride;
-  r.nptnr = d.nptnr + rr * (N + 3);
-  r.ctype = d.ctype + rr * (N + 3);
+  r.cal = d.cal + rr * d.cal_stride;
   r.er34 = d.er34 + rr * 2 * N;
   r.up = d.up + rr * N * s->cap;
   r.dn = d.dn + rr * N * s->cap;
@@ -71,15 +85,11 @@ DMD_DEV void rep_bind(Rep& r, const DevArrays& d, const PairTables* tab, int rid
   r.cellof = d.cellof + rr * N;
   r.tmin1 = d.tmin1 + rr * s->ngroups;
   r.sc = d.scal + rr;
-  r.log = d.log + rr * s->log_cap;
+  r.log = d.log + rr * (s->log_cap > 0 ? s->log_cap : 1);
   r.out = d.out + rr * s->out_cap;
-  const RepScalars& q = *r.sc;
-  r.t = q.t; r.tfalse = q.tfalse; r.old_tfalse = q.old_tfalse; r.setemp = q.setemp; r.interval = q.interval;
-  r.t_fact = q.t_fact; r.interval_max = q.interval_max; r.n_forced = q.n_forced; r.avegtime = q.avegtime;
-  r.coll = q.coll; r.seed = q.rng_seed; r.ctr = q.rng_ctr;
-  r.n_pair_pred = q.n_pair_pred; r.n_nbr_visits = q.n_nbr_visits;
-  r.n_log = q.n_log; r.n_out = q.n_out; r.error = q.error; r.error_info = q.error_info;
-  r.ndirty = 0;
+  r.cq = cq;
+  r.dirty0 = r.dirty1 = 0;
+  rep_load_scalars(r);
 }
 
 DMD_DEV void rep_save(Rep& r) {
@@ -100,61 +110,78 @@ DMD_DEV void set_error(Rep& r, int code, int info) {
   }
 }
 
-DMD_DEV int pair_static_code(const Rep& r, int a, int b) {
-  return static_code(*r.c.sys, r.c.meta[a], r.c.chain[a], a, r.c.meta[b], r.c.chain[b], b);
-}
-
 // ---------------------------------------------------------------------------------------------------------
-// calendar: tim[] in groups of 32 with a per-group minimum tmin1[]; the event to process is the global
-// arg-min (ties -> lowest bead index).  Replaces the bucket lists of add_tbin.f / del_tbin.f; dropping the
-// "tim < interval_max" filter is semantics-neutral (SURVEY.md 8a note C).
+// calendar: cal[] in groups of 32 entries with a per-group minimum tmin1[]; the event to process is the
+// global arg-min (ties -> lowest bead index).  Replaces the bucket lists of add_tbin.f / del_tbin.f;
+// dropping the "tim < interval_max" filter is semantics-neutral (SURVEY.md 8a note C).
 // ---------------------------------------------------------------------------------------------------------
-DMD_DEV void mark_dirty(Rep& r, int g);
-
 DMD_DEV void group_min_update(Rep& r, int g) {
   double v = T_PAD;
   for (int q = Warp::lane(); q < 32; q += DMD_W) {
-    double x = r.tim[g * 32 + q];
+    double x = r.cal[g * 32 + q].t;
     if (x < v) v = x;
   }
-  int key = 0;
-  warp_argmin(v, key);
+#if DMD_W > 1
+#pragma unroll
+  for (int m = DMD_W / 2; m >= 1; m >>= 1) {
+    double ov = Warp::shfl_xor(v, m);
+    if (ov < v) v = ov;
+  }
+#endif
   if (Warp::lane() == 0) r.tmin1[g] = v;
+}
+
+DMD_DEV void mark_dirty(Rep& r, int g) {  // g warp-uniform
+  if (g < 64) r.dirty0 |= 1ull << g;
+  else if (g < 128) r.dirty1 |= 1ull << (g - 64);
+  else {  // very large systems: refresh immediately
+    Warp::sync();
+    group_min_update(r, g);
+  }
 }
 
 DMD_DEV void flush_dirty(Rep& r) {
   Warp::sync();
-  for (int k = 0; k < r.ndirty; k++) group_min_update(r, r.dirty[k]);
-  r.ndirty = 0;
+  while (r.dirty0) {
+#if defined(DMD_HOST_TRACE)
+    int g = __builtin_ctzll(r.dirty0);
+#else
+    int g = __ffsll((long long)r.dirty0) - 1;
+#endif
+    r.dirty0 &= r.dirty0 - 1;
+    group_min_update(r, g);
+  }
+  while (r.dirty1) {
+#if defined(DMD_HOST_TRACE)
+    int g = __builtin_ctzll(r.dirty1);
+#else
+    int g = __ffsll((long long)r.dirty1) - 1;
+#endif
+    r.dirty1 &= r.dirty1 - 1;
+    group_min_update(r, 64 + g);
+  }
   Warp::sync();
 }
 
-DMD_DEV void mark_dirty(Rep& r, int g) {  // g must be warp-uniform
-  for (int k = 0; k < r.ndirty; k++)
-    if (r.dirty[k] == g) return;
-  if (r.ndirty == MAX_DIRTY) flush_dirty(r);
-  r.dirty[r.ndirty++] = g;
-}
-
-// every lane may have changed tim[l] of a different bead l (l < 0: none): record the groups warp-uniformly
+// every lane may have changed the entry of a different bead l (l < 0: none): record the groups uniformly
 DMD_DEV void mark_dirty_lanes(Rep& r, int l) {
   unsigned m = Warp::ballot(l >= 0);
   while (m) {
     int src = dmd_ffs(m) - 1;
     m &= m - 1;
-    int ll = Warp::shfl(l, src);
-    mark_dirty(r, ll >> 5);
+    mark_dirty(r, Warp::shfl(l, src) >> 5);
   }
 }
 
 DMD_DEV void rebuild_all_groups(Rep& r) {
   Warp::sync();
   for (int g = 0; g < r.G; g++) group_min_update(r, g);
-  r.ndirty = 0;
+  r.dirty0 = r.dirty1 = 0;
   Warp::sync();
 }
 
-DMD_DEV int pop_min(Rep& r, double& tmin) {
+// returns the owner index of the earliest entry (or -1) and the entry itself
+DMD_DEV int pop_min(Rep& r, CalEnt& ev) {
   double best = T_PAD;
   int bg = 0x7fffffff;
   for (int g = Warp::lane(); g < r.G; g += DMD_W) {
@@ -167,63 +194,125 @@ DMD_DEV int pop_min(Rep& r, double& tmin) {
   warp_argmin(best, bg);
   if (bg == 0x7fffffff || !(best < 1e299)) return -1;
   double v = T_PAD;
-  int key = 0x7fffffff;
+  int key = 0x7fffffff, pt = -1, ty = -1;
   for (int q = Warp::lane(); q < 32; q += DMD_W) {
-    double x = r.tim[bg * 32 + q];
-    if (x < v) {
-      v = x;
+    CalEnt e = r.cal[bg * 32 + q];
+    if (e.t < v) {
+      v = e.t;
       key = q;
+      pt = e.ptnr;
+      ty = e.type;
     }
   }
-  warp_argmin(v, key);
-  tmin = v;
-  return bg * 32 + key;
+  double wv = v;
+  int wkey = key;
+  warp_argmin(wv, wkey);
+#if DMD_W > 1
+  const int src = wkey & 31;  // the owning lane (one entry per lane when DMD_W == 32)
+  pt = Warp::shfl(pt, src);
+  ty = Warp::shfl(ty, src);
+#endif
+  ev.t = wv;
+  ev.ptnr = pt;
+  ev.type = ty;
+  return bg * 32 + wkey;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// prediction
-// ---------------------------------------------------------------------------------------------------------
-// partner candidate p of bead l: p < nup -> up-list entry; else aux slot p - nup (extra_repuls(l,1:3) > l)
-DMD_DEV bool eval_candidate(Rep& r, int l, const BeadRec& rl, uint32_t ml, int nu, int er3, int p, double& tij,
-                            int& type, int& j) {
-  int sc;
-  if (p < nu) {
-    uint32_t e = r.up[(size_t)l * r.cap + p];
-    j = (int)(e & NB_MASK);
-    sc = (int)(e >> NB_SHIFT);
-  } else {
-    int k = p - nu;
-    j = k == 0 ? rl.er1 : (k == 1 ? rl.er2 : er3);
-    if (j <= l) return false;  // events.f:77 (also rejects the empty slot, -1)
-    sc = 1;                    // auxiliary pairs are always static class 1 (events.f:80-84)
-  }
-  const BeadRec rj = r.rec[j];
-  int code = overlay_code(sc, l, rl, j, rj);
-  tij = T_NONE;
-  type = -1;
-  pair_time(r.c, code, rl, rj, ml, rl.bptnr == j, r.tfalse, tij, type);
-  return true;
-}
+DMD_DEV int pack_type(int type, int sc) { return (type & 0xff) | (sc << 8); }
+DMD_DEV int type_of(int packed) { return (int)(int8_t)(packed & 0xff); }
+DMD_DEV int sc_of(int packed) { return (packed >> 8) & 0xff; }
 
-// the block repeated throughout partial_events.f (e.g. :16-35): full re-prediction of bead l over its
-// up-list and aux slots, lanes over candidates.
-DMD_DEV void redo_full(Rep& r, int l) {
-  const BeadRec rl = r.rec[l];
-  const uint32_t ml = r.c.meta[l];
-  const int nu = r.nup[l];
-  const int er3 = r.er34[2 * l];
-  const int total = nu + 3;
+// ---------------------------------------------------------------------------------------------------------
+// prediction pass for bead a (hot): lanes cover, in this order,
+//   [0, nu)            up-list partners j > a          } events.f:26-57 / eventredo_up.f : owner a
+//   [nu, nu+3)         aux slots extra_repuls(a,1:3)>a }
+//   [nF, nF+nd)        down-list beads l < a           } eventredo_down.f : owner l, or cascade when
+//   [nF+nd, nF+nd+3)   aux slots extra_repuls(a,1:3)<a }   nptnr(l) == a (partial_events.f:73-96)
+// with_down = false restricts the pass to the first two ranges (a cascaded full re-prediction).
+// Lanes of the last two ranges that need a cascade push their bead on the queue r.cq.
+// ---------------------------------------------------------------------------------------------------------
+DMD_DEV void predict_pass(Rep& r, int a, bool with_down, int skip, int& cqn) {
+  const BeadRec ra = r.rec[a];
+  const uint32_t ma = r.c.meta[a];
+  const int nu = r.nup[a];
+  const int nd = with_down ? (int)r.ndn[a] : 0;
+  const int er3 = r.er34[2 * a];
+  const int nF = nu + 3, total = with_down ? nF + nd + 3 : nF;
   double best = r.interval_max + LTSTEP - r.tfalse;
   int bpos = 0x7fffffff, bj = -1, btype = -1;
-  for (int p = Warp::lane(); p < total; p += DMD_W) {
-    double tij;
-    int type, j;
-    if (eval_candidate(r, l, rl, ml, nu, er3, p, tij, type, j)) {
-      if (tij < best) {  // strict: first in evaluation order wins (events.f:53)
-        best = tij;
-        bpos = p;
-        bj = j;
-        btype = type;
+  r.n_pair_pred += total;
+  r.n_nbr_visits += nu + nd;
+  for (int base = 0; base < total; base += DMD_W) {
+    const int p = base + Warp::lane();
+    int b = -1, sc = 1;  // the other bead of the pair and the pair's static class
+    bool full = p < nF;
+    if (p < nu) {
+      uint32_t e = r.up[(size_t)a * r.cap + p];
+      b = (int)(e & NB_MASK);
+      sc = (int)(e >> NB_SHIFT);
+    } else if (p < nF) {
+      int k = p - nu;
+      b = k == 0 ? ra.er1 : (k == 1 ? ra.er2 : er3);
+      if (b <= a) b = -1;  // events.f:77
+    } else if (p < nF + nd) {
+      uint32_t e = r.dn[(size_t)a * r.cap + (p - nF)];
+      b = (int)(e & NB_MASK);
+      sc = (int)(e >> NB_SHIFT);
+      if (b == skip) b = -1;  // partial_events.f:136
+    } else if (p < total) {
+      int k = p - nF - nd;
+      b = k == 0 ? ra.er1 : (k == 1 ? ra.er2 : er3);
+      if (!(b >= 0 && b < a)) b = -1;  // partial_events.f:100,166
+    }
+    bool need_full = false;
+    int changed = -1;
+    if (b >= 0) {
+      CalEnt eb;
+      eb.t = 0.0; eb.ptnr = -1; eb.type = -1;
+      if (!full) eb = r.cal[b];
+      if (!full && eb.ptnr == a) {
+        need_full = true;  // l's next event was with a: full re-prediction of l (cascade)
+      } else {
+        const BeadRec rb = r.rec[b];
+        const int code = overlay_code(sc, a, ra, b, rb);
+        double tij = T_NONE;
+        int type = -1;
+        {  // one prediction site for both orientations (owner = lower index: a when full, b otherwise)
+          const Geom g = pair_geom(ra, rb, r.tfalse);
+          const double rijsq = g.rx * g.rx + g.ry * g.ry + g.rz * g.rz;
+          const double vijsq = g.vx * g.vx + g.vy * g.vy + g.vz * g.vz;
+          const int idlo = full ? ra.ident : rb.ident, idhi = full ? rb.ident : ra.ident;
+          const uint32_t mlo = full ? ma : r.c.meta[b];
+          const bool bonded = full ? ra.bptnr == b : rb.bptnr == a;
+          pair_time_core(r.c, code, g.bij, rijsq, vijsq, idlo, idhi, mlo, bonded, tij, type);
+        }
+        if (full) {
+          if (tij < best) {  // strict: first in evaluation order wins (events.f:53)
+            best = tij;
+            bpos = p;
+            bj = b;
+            btype = pack_type(type, sc);
+          }
+        } else {  // eventredo_down.f:70-77
+          tij = tij + r.tfalse;
+          if (tij < eb.t) {
+            CalEnt ne;
+            ne.t = tij;
+            ne.ptnr = a;
+            ne.type = pack_type(type, sc);
+            r.cal[b] = ne;
+            changed = b;
+          }
+        }
+      }
+    }
+    if (with_down) {
+      mark_dirty_lanes(r, changed);
+      unsigned m = Warp::ballot(need_full);
+      if (m) {
+        int pos = cqn + dmd_popc(m & ((1u << Warp::lane()) - 1u));
+        if (need_full && pos < CQ_CAP) r.cq[pos] = b;
+        cqn += dmd_popc(m);
       }
     }
   }
@@ -239,14 +328,54 @@ DMD_DEV void redo_full(Rep& r, int l) {
     bj = -1;
     btype = -1;
   }
-  r.n_pair_pred += total;
-  r.n_nbr_visits += nu;
   if (Warp::lane() == 0) {
-    r.tim[l] = wbest + r.tfalse;
-    r.nptnr[l] = bj;
-    r.ctype[l] = (int8_t)btype;
+    CalEnt ne;
+    ne.t = wbest + r.tfalse;
+    ne.ptnr = bj;
+    ne.type = btype;
+    r.cal[a] = ne;
   }
-  mark_dirty(r, l >> 5);
+  mark_dirty(r, a >> 5);
+}
+
+// partial_events.f:16-201.  Order used: full(i), down(i) [+cascades], full(j), down(j) [+cascades]; this is
+// equivalent to the Fortran's full(i), full(j), down(i), down(j) because full(j) only rewrites entry j, which
+// down(i) never reads (its beads are < i < j), see DESIGN.md "pass order".
+DMD_DEV void repuls_del_b(Rep& r, int n, int cb);
+
+DMD_DEV void partial_events(Rep& r, int i, int j, bool xpulse_del) {
+  Warp::sync();
+  int cqn = 0, stage = 0;
+  while (true) {
+    int a, skip = -1;
+    bool with_down;
+    if (cqn > 0) {
+      if (cqn > CQ_CAP) {
+        set_error(r, DMD_E_NBR_CAP, cqn);
+        break;
+      }
+      Warp::sync();
+      a = r.cq[--cqn];
+      with_down = false;
+    } else if (stage < 2) {
+      a = stage == 0 ? i : j;
+      skip = stage == 0 ? -1 : i;
+      stage++;
+      if (a < 0) continue;
+      with_down = true;
+    } else {
+      break;
+    }
+    predict_pass(r, a, with_down, skip, cqn);
+    Warp::sync();
+  }
+  if (xpulse_del) {
+    if (Warp::lane() == 0) {
+      if (r.rec[i].ident < r.rec[j].ident) repuls_del_b(r, i, j);
+      else repuls_del_b(r, j, i);
+    }
+    Warp::sync();
+  }
 }
 
 // one lane does the whole list of bead l (bulk path: events.f:23-107 with one lane per bead)
@@ -258,79 +387,39 @@ DMD_DEV void redo_lane(Rep& r, int l) {
   double best = r.interval_max + LTSTEP - r.tfalse;
   int bj = -1, btype = -1;
   for (int p = 0; p < nu + 3; p++) {
-    double tij;
-    int type, j;
-    if (eval_candidate(r, l, rl, ml, nu, er3, p, tij, type, j)) {
-      if (tij < best) {
-        best = tij;
-        bj = j;
-        btype = type;
-      }
+    int j, sc = 1;
+    if (p < nu) {
+      uint32_t e = r.up[(size_t)l * r.cap + p];
+      j = (int)(e & NB_MASK);
+      sc = (int)(e >> NB_SHIFT);
+    } else {
+      int k = p - nu;
+      j = k == 0 ? rl.er1 : (k == 1 ? rl.er2 : er3);
+      if (j <= l) continue;
+    }
+    const BeadRec rj = r.rec[j];
+    const int code = overlay_code(sc, l, rl, j, rj);
+    double tij = T_NONE;
+    int type = -1;
+    pair_time(r.c, code, rl, rj, ml, rl.bptnr == j, r.tfalse, tij, type);
+    if (tij < best) {
+      best = tij;
+      bj = j;
+      btype = pack_type(type, sc);
     }
   }
-  r.tim[l] = best + r.tfalse;
-  r.nptnr[l] = bj;
-  r.ctype[l] = (int8_t)btype;
+  CalEnt ne;
+  ne.t = best + r.tfalse;
+  ne.ptnr = bj;
+  ne.type = btype;
+  r.cal[l] = ne;
 }
 
-// events.f:23-123 for the whole replica (caller has reset nothing: every bead is re-derived)
+// events.f:23-123 for the whole replica (every bead is re-derived from interval_max + ltstep)
 DMD_DEV void predict_all(Rep& r) {
   Warp::sync();
   for (int l = Warp::lane(); l < r.N; l += DMD_W) redo_lane(r, l);
   rebuild_all_groups(r);
-}
-
-// partial_events.f:68-123 / :130-189: every lower-index neighbour l of bead a (down-list + aux slots)
-DMD_DEV void down_phase(Rep& r, int a, int skip) {
-  const BeadRec ra = r.rec[a];
-  const int nd = r.ndn[a];
-  const int er3 = r.er34[2 * a];
-  const int total = nd + 3;
-  r.n_nbr_visits += nd;
-  r.n_pair_pred += total;
-  for (int base = 0; base < total; base += DMD_W) {
-    const int p = base + Warp::lane();
-    int l = -1, sc = 1;
-    if (p < nd) {
-      uint32_t e = r.dn[(size_t)a * r.cap + p];
-      l = (int)(e & NB_MASK);
-      sc = (int)(e >> NB_SHIFT);
-      if (l == skip) l = -1;  // partial_events.f:136
-    } else if (p < total) {
-      int k = p - nd;
-      l = k == 0 ? ra.er1 : (k == 1 ? ra.er2 : er3);
-      if (!(l >= 0 && l < a)) l = -1;  // partial_events.f:100,166
-    }
-    bool need_full = false;
-    int changed = -1;
-    if (l >= 0) {
-      if (r.nptnr[l] != a) {  // eventredo_down.f:25-78
-        const BeadRec rl = r.rec[l];
-        int code = overlay_code(sc, l, rl, a, ra);
-        double tij = T_NONE;
-        int type = -1;
-        pair_time(r.c, code, rl, ra, r.c.meta[l], rl.bptnr == a, r.tfalse, tij, type);
-        tij = tij + r.tfalse;
-        if (tij < r.tim[l]) {
-          r.tim[l] = tij;
-          r.nptnr[l] = a;
-          r.ctype[l] = (int8_t)type;
-          changed = l;
-        }
-      } else {
-        need_full = true;
-      }
-    }
-    mark_dirty_lanes(r, changed);
-    unsigned m = Warp::ballot(need_full);
-    Warp::sync();
-    while (m) {  // cascade: l's next event was with a -> full re-prediction of l
-      int src = dmd_ffs(m) - 1;
-      m &= m - 1;
-      int lf = Warp::shfl(l, src);
-      redo_full(r, lf);
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -403,27 +492,6 @@ DMD_DEV void repuls_del_b(Rep& r, int n, int cb) {
   r.er34[2 * cb + 1] = -1;
 }
 
-// partial_events.f:16-201
-DMD_DEV void partial_events(Rep& r, int i, int j, bool xpulse_del) {
-  Warp::sync();
-  redo_full(r, i);
-  if (j >= 0) redo_full(r, j);
-  Warp::sync();
-  down_phase(r, i, -1);
-  if (j >= 0) {
-    Warp::sync();
-    down_phase(r, j, i);
-  }
-  Warp::sync();
-  if (xpulse_del) {
-    if (Warp::lane() == 0) {
-      if (r.rec[i].ident < r.rec[j].ident) repuls_del_b(r, i, j);
-      else repuls_del_b(r, j, i);
-    }
-    Warp::sync();
-  }
-}
-
 DMD_DEV void log_event(Rep& r, int i, int j, int type, int code) {
   if (r.n_log < r.c.sys->log_cap) {
     if (Warp::lane() == 0) {
@@ -456,19 +524,21 @@ DMD_DEV int aux_clear_count(Rep& r, int n, int cb, int excl) {
   return warp_sum(cnt);
 }
 
-// worker block main.F90:1429-1959 with current state, then master main.F90:926,943
-DMD_DEV void pair_event(Rep& r, int i) {
+// ---- cold part of a pair event: H-bond related types (anything but core / bond events), < 1 % of events.
+// Resolution main.F90:1487-1634, eventdyn.f (types 4-13) / bumped.f, bookkeeping main.F90:1638-1937.
+// Takes the replica view by value (the hot loop keeps its copy in registers); rng counter goes through r.sc.
+struct ColdRes {
+  int ct;
+  int xpulse;
+  uint64_t ctr;
+};
+DMD_COLD ColdRes pair_event_cold(Rep r, int i, int j, int ct, int code) {
   const SysConst& s = *r.c.sys;
-  const int j = r.nptnr[i];
-  int ct = r.ctype[i];
   BeadRec ri = r.rec[i], rj = r.rec[j];
   const uint32_t mi = r.c.meta[i], mj = r.c.meta[j];
-  const int code = overlay_code(pair_static_code(r, i, j), i, ri, j, rj);  // ev_code(i,j), main.F90:587
   const bool bonded = ri.bptnr == j;
   const bool tok = !is_terminal_bead(s, mi) && !is_terminal_bead(s, mj);
   const int er4i = r.er34[2 * i + 1], er4j = r.er34[2 * j + 1];
-  bool xpulse_del = false;
-  // ---- resolution of provisional types, main.F90:1487-1634
   if (ct == 7) {
     if (er4i < 0 && er4j < 0) {
       if (tok) {
@@ -482,7 +552,7 @@ DMD_DEV void pair_event(Rep& r, int i) {
       ct = 9;
     }
   } else if (ct == 10 || ct == 12) {
-    const int x = code < 45 ? i : j;     // the H-bond bead of the auxiliary pair
+    const int x = code < 45 ? i : j;      // the H-bond bead of the auxiliary pair
     const int other = code < 45 ? j : i;  // the auxiliary bead
     const int hb = code < 45 ? er4i : er4j;
     if (hb < 0) {
@@ -493,28 +563,24 @@ DMD_DEV void pair_event(Rep& r, int i) {
       if (ct == 10) {
         int n = rx.ident < rh.ident ? x : hb, cb = rx.ident < rh.ident ? hb : x;
         ct = aux_clear_count(r, n, cb, other) == 3 ? 5 : 15;  // repuls_check_3.f:98-102
+      } else if (rx.bptnr == hb) {  // check_sigma.f:12-29
+        Geom g = pair_geom(rx, rh, r.tfalse);
+        double rijsq = g.rx * g.rx + g.ry * g.ry + g.rz * g.rz;
+        double diff = rijsq - r.c.tab->sigma_sq[tix(rx.ident, rh.ident)];
+        ct = diff < 0.0 ? 13 : 6;
       } else {
-        if (rx.bptnr == hb) {  // check_sigma.f:12-29
-          Geom g = pair_geom(rx, rh, r.tfalse);
-          double rijsq = g.rx * g.rx + g.ry * g.ry + g.rz * g.rz;
-          double diff = rijsq - r.c.tab->sigma_sq[tix(rx.ident, rh.ident)];
-          ct = diff < 0.0 ? 13 : 6;
-        } else {
-          ct = 15;
-        }
+        ct = 15;
       }
     }
   }
-  // ---- dynamics, main.F90:1636 / :1829,1881,1884
-  if (ct < 14) ct = event_dynamics(r.c, ct, code, ri, rj, mi, bonded, r.tfalse);
-  else bump_off(r.c, code, ri, rj, r.tfalse);
+  if (ct < 14) ct = event_dynamics(r.c, ct, code, ri, rj, mi, bonded, r.tfalse);  // main.F90:1636
+  else bump_off(r.c, code, ri, rj, r.tfalse);                                       // :1829,1881,1884
   Warp::sync();
   if (Warp::lane() == 0) {
     BeadRec* pi = &r.rec[i];
     BeadRec* pj = &r.rec[j];
     pi->x = ri.x; pi->y = ri.y; pi->z = ri.z; pi->vx = ri.vx; pi->vy = ri.vy; pi->vz = ri.vz;
     pj->x = rj.x; pj->y = rj.y; pj->z = rj.z; pj->vx = rj.vx; pj->vy = rj.vy; pj->vz = rj.vz;
-    // ---- bookkeeping, main.F90:1638-1937
     const int n = ri.ident < rj.ident ? i : j, cb = ri.ident < rj.ident ? j : i;
     if (ct == 20) {
       if (ri.ident + rj.ident == 5) {
@@ -552,57 +618,41 @@ DMD_DEV void pair_event(Rep& r, int i) {
       if (tok) repuls_del_a(r, n, cb);
     }
   }
-  if ((ct == 21 && ri.ident <= 8 && tok) || (ct == 16 && tok)) xpulse_del = true;
+  ColdRes res;
+  res.xpulse = ((ct == 21 && ri.ident <= 8 && tok) || (ct == 16 && tok)) ? 1 : 0;
+  res.ct = ct;
+  res.ctr = r.ctr;
+  Warp::sync();
+  return res;
+}
+
+// worker block main.F90:1429-1959 with current state, then master main.F90:926,943
+DMD_DEV void pair_event(Rep& r, int i, const CalEnt& ev) {
+  const int j = ev.ptnr;
+  int ct = type_of(ev.type);
+  bool xpulse_del = false;
+  int code;
+  if (ct >= 1 && ct <= 3) {  // hot: hard-core and bond events (> 99 % of all events)
+    BeadRec ri = r.rec[i], rj = r.rec[j];
+    code = overlay_code(sc_of(ev.type), i, ri, j, rj);  // ev_code(i,j), main.F90:587
+    ct = event_dynamics_hot(r.c, ct, code, ri, rj, r.c.meta[i], ri.bptnr == j, r.tfalse);
+    Warp::sync();
+    if (Warp::lane() == 0) {
+      BeadRec* pi = &r.rec[i];
+      BeadRec* pj = &r.rec[j];
+      pi->x = ri.x; pi->y = ri.y; pi->z = ri.z; pi->vx = ri.vx; pi->vy = ri.vy; pi->vz = ri.vz;
+      pj->x = rj.x; pj->y = rj.y; pj->z = rj.z; pj->vx = rj.vx; pj->vy = rj.vy; pj->vz = rj.vz;
+    }
+  } else {
+    code = overlay_code(sc_of(ev.type), i, r.rec[i], j, r.rec[j]);
+    ColdRes cr = pair_event_cold(r, i, j, ct, code);
+    ct = cr.ct;
+    xpulse_del = cr.xpulse != 0;
+    r.ctr = cr.ctr;
+  }
   if (Warp::lane() == 0 && ct >= 0 && ct < 32) r.sc->nevents[ct] += 1;  // main.F90:926
   log_event(r, i, j, ct, code);
   partial_events(r, i, j, xpulse_del);  // main.F90:943
-}
-
-// main.F90:997-1049
-DMD_DEV void ghost_event(Rep& r) {
-  const int N = r.N;
-  int i;
-  do {
-    i = (int)(rng_uniform(r.seed, r.ctr) * N);
-  } while (i == N);
-  BeadRec b = r.rec[i];
-  const double bmi = r.c.sys->bmass[b.ident];
-  b.x = b.x + b.vx * r.tfalse;
-  b.y = b.y + b.vy * r.tfalse;
-  b.z = b.z + b.vz * r.tfalse;
-  double v1, v2, rr, fact;
-  do {
-    v1 = 2.0 * rng_uniform(r.seed, r.ctr) - 1.0;
-    v2 = 2.0 * rng_uniform(r.seed, r.ctr) - 1.0;
-    rr = v1 * v1 + v2 * v2;
-  } while (rr == 0.0 || rr >= 1.0);
-  fact = dmd_sqrt(-2.0 * r.setemp * bmi * dmd_log(rr) / rr);
-  b.vx = v1 * fact / bmi;
-  b.vy = v2 * fact / bmi;
-  do {
-    v1 = 2.0 * rng_uniform(r.seed, r.ctr) - 1.0;
-    v2 = 2.0 * rng_uniform(r.seed, r.ctr) - 1.0;
-    rr = v1 * v1 + v2 * v2;
-  } while (rr == 0.0 || rr >= 1.0);
-  fact = dmd_sqrt(-2.0 * r.setemp * bmi * dmd_log(rr) / rr);
-  b.vz = v1 * fact / bmi;
-  b.x = b.x - b.vx * r.tfalse;
-  b.y = b.y - b.vy * r.tfalse;
-  b.z = b.z - b.vz * r.tfalse;
-  double tgho = 0.0;
-  while (tgho < 1e-18 || tgho == 1.0) tgho = rng_uniform(r.seed, r.ctr);
-  const double tnext = -1.0 * dmd_log(tgho) * r.avegtime + r.tfalse;
-  Warp::sync();
-  if (Warp::lane() == 0) {
-    BeadRec* p = &r.rec[i];
-    p->x = b.x; p->y = b.y; p->z = b.z; p->vx = b.vx; p->vy = b.vy; p->vz = b.vz;
-    r.tim[N] = tnext;
-    r.sc->numghosts += 1;
-  }
-  mark_dirty(r, N >> 5);
-  if (r.tfalse < r.old_tfalse) r.tfalse = r.old_tfalse;  // main.F90:1047
-  log_event(r, N, i, -2, 0);
-  partial_events(r, i, -1, false);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -728,14 +778,64 @@ DMD_DEV void nbor(Rep& r) {  // nbor.f:33-137
   cell_clear(r);
 }
 
+// ---- cold pseudo-events: they work on a by-value copy of the view and hand the scalars back through r.sc
+// main.F90:997-1049
+DMD_COLD void ghost_event_cold(Rep r) {
+  const int N = r.N;
+  int i;
+  do {
+    i = (int)(rng_uniform(r.seed, r.ctr) * N);
+  } while (i == N);
+  BeadRec b = r.rec[i];
+  const double bmi = r.c.sys->bmass[b.ident];
+  b.x = b.x + b.vx * r.tfalse;
+  b.y = b.y + b.vy * r.tfalse;
+  b.z = b.z + b.vz * r.tfalse;
+  double v1, v2, rr, fact;
+  do {
+    v1 = 2.0 * rng_uniform(r.seed, r.ctr) - 1.0;
+    v2 = 2.0 * rng_uniform(r.seed, r.ctr) - 1.0;
+    rr = v1 * v1 + v2 * v2;
+  } while (rr == 0.0 || rr >= 1.0);
+  fact = dmd_sqrt(-2.0 * r.setemp * bmi * dmd_log(rr) / rr);
+  b.vx = v1 * fact / bmi;
+  b.vy = v2 * fact / bmi;
+  do {
+    v1 = 2.0 * rng_uniform(r.seed, r.ctr) - 1.0;
+    v2 = 2.0 * rng_uniform(r.seed, r.ctr) - 1.0;
+    rr = v1 * v1 + v2 * v2;
+  } while (rr == 0.0 || rr >= 1.0);
+  fact = dmd_sqrt(-2.0 * r.setemp * bmi * dmd_log(rr) / rr);
+  b.vz = v1 * fact / bmi;
+  b.x = b.x - b.vx * r.tfalse;
+  b.y = b.y - b.vy * r.tfalse;
+  b.z = b.z - b.vz * r.tfalse;
+  double tgho = 0.0;
+  while (tgho < 1e-18 || tgho == 1.0) tgho = rng_uniform(r.seed, r.ctr);
+  const double tnext = -1.0 * dmd_log(tgho) * r.avegtime + r.tfalse;
+  Warp::sync();
+  if (Warp::lane() == 0) {
+    BeadRec* p = &r.rec[i];
+    p->x = b.x; p->y = b.y; p->z = b.z; p->vx = b.vx; p->vy = b.vy; p->vz = b.vz;
+    r.cal[N].t = tnext;
+    r.sc->numghosts += 1;
+  }
+  mark_dirty(r, N >> 5);
+  if (r.tfalse < r.old_tfalse) r.tfalse = r.old_tfalse;  // main.F90:1047
+  log_event(r, N, i, -2, 0);
+  partial_events(r, i, -1, false);
+  flush_dirty(r);
+  rep_save(r);
+}
+
 // main.F90:1126-1187
-DMD_DEV void interval_event(Rep& r) {
+DMD_COLD void interval_event_cold(Rep r) {
   const SysConst& s = *r.c.sys;
   const int N = r.N;
   const double tf = r.tfalse;
   r.t = r.t + tf;
   Warp::sync();
-  for (int k = Warp::lane(); k < N + 3; k += DMD_W) r.tim[k] = r.tim[k] - tf;  // :1133-1135
+  for (int k = Warp::lane(); k < N + 3; k += DMD_W) r.cal[k].t = r.cal[k].t - tf;  // :1133-1135
   r.interval_max = r.interval_max - tf;
   double moved_far = 0.0;
   for (int k = Warp::lane(); k < N; k += DMD_W) {  // :1140-1144 + displ.f:20-33
@@ -775,10 +875,11 @@ DMD_DEV void interval_event(Rep& r) {
     nbor(r);
     predict_all(r);  // events(); every bead's (tim, nptnr, coltype) is re-derived from interval_max+ltstep
   }
-  if (Warp::lane() == 0) r.tim[N + 1] = r.interval * 0.999;  // :1181
+  if (Warp::lane() == 0) r.cal[N + 1].t = r.interval * 0.999;  // :1181
   Warp::sync();
   rebuild_all_groups(r);
   log_event(r, N + 1, -1, -2, 0);
+  rep_save(r);
 }
 
 // energy.f:25-101 on the neighbour lists instead of the O(N^2) ev_code scan (rl(16) >= every well diameter
@@ -836,7 +937,7 @@ DMD_DEV void energy_of(Rep& r, OutRec& o) {
 }
 
 // main.F90:1191-1246
-DMD_DEV void output_event(Rep& r) {
+DMD_COLD void output_event_cold(Rep r) {
   const int N = r.N;
   OutRec o;
   energy_of(r, o);
@@ -844,26 +945,35 @@ DMD_DEV void output_event(Rep& r) {
     if (Warp::lane() == 0) r.out[r.n_out] = o;
     r.n_out++;
   }
-  if (Warp::lane() == 0) r.tim[N + 2] = 3.3 / (dmd_sqrt(r.setemp)) + 5 + r.tfalse;
+  if (Warp::lane() == 0) r.cal[N + 2].t = 3.3 / (dmd_sqrt(r.setemp)) + 5 + r.tfalse;
   mark_dirty(r, (N + 2) >> 5);
   log_event(r, N + 2, -1, -2, 0);
+  flush_dirty(r);
+  rep_save(r);
 }
 
 // one iteration of main.F90:484-1258 with serial semantics
 DMD_DEV bool step(Rep& r) {
   flush_dirty(r);
-  double tmin;
-  const int o = pop_min(r, tmin);
+  CalEnt ev;
+  const int o = pop_min(r, ev);
   if (o < 0) {
     set_error(r, DMD_E_CAL_EMPTY, 0);
     return false;
   }
-  r.tfalse = tmin;
+  r.tfalse = ev.t;
   r.coll += 1;
-  if (o < r.N) pair_event(r, o);
-  else if (o == r.N) ghost_event(r);
-  else if (o == r.N + 1) interval_event(r);
-  else output_event(r);
+  if (o < r.N) {
+    pair_event(r, o, ev);
+  } else {
+    rep_save(r);  // hand the scalars to the out-of-line handler through r.sc ...
+    if (o == r.N) ghost_event_cold(r);
+    else if (o == r.N + 1) interval_event_cold(r);
+    else output_event_cold(r);
+    Warp::sync();
+    rep_load_scalars(r);  // ... and take them back
+    r.dirty0 = r.dirty1 = 0;
+  }
   r.old_tfalse = r.tfalse;
   return r.error == 0;
 }

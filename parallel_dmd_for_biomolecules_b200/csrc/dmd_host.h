@@ -28,9 +28,7 @@ struct HostReplicaInit {  // everything dmdb_set_state uploads for one replica
   std::vector<BeadRec> rec;
   std::vector<int32_t> er34;
   std::vector<double> oldr;
-  std::vector<double> tim;     // tim_stride entries (padded with 1e300)
-  std::vector<int32_t> nptnr;  // N+3
-  std::vector<int8_t> ctype;   // N+3
+  std::vector<CalEnt> cal;     // cal_stride entries (padding t = 1e300)
   RepScalars scal;
 };
 
@@ -271,7 +269,7 @@ inline void host_repuls_add(const HostModel& m, HostReplicaInit& h, int n, int c
 // run start for one replica: inputinfo.f:89-91 (wrap), main.F90:143-156 (time constants), :205-234 (reset),
 // :241-321 (restart fix-up from bptnr), :408-423 (pseudo-event times; the ghost time is drawn on the device).
 inline void build_replica_init(const HostModel& m, const double* sv, const int32_t* bptnr1, double tstar, uint64_t seed,
-                               int tim_stride, HostReplicaInit& h) {
+                               int cal_stride, HostReplicaInit& h) {
   const SysConst& s = m.sys;
   const int N = s.N;
   h.rec.assign(N, BeadRec());
@@ -325,14 +323,14 @@ inline void build_replica_init(const HostModel& m, const double* sv, const int32
   q.interval_max = q.n_forced * q.interval;
   q.avegtime = 0.00005 / std::sqrt(q.setemp);    // main.F90:156
   q.rng_seed = seed;
-  h.tim.assign(tim_stride, 1e300);
-  h.nptnr.assign(N + 3, -1);
-  h.ctype.assign(N + 3, -1);
-  for (int k = 0; k < N; k++) h.tim[k] = q.interval_max + 1e-10;  // main.F90:212
-  h.tim[N] = 1000000000.0;                       // ghost: drawn on the device when canon (main.F90:408-416)
-  h.tim[N + 1] = q.interval;                     // main.F90:421
-  h.tim[N + 2] = 3.3 / (std::sqrt(q.setemp)) + 5;  // main.F90:423
-  for (int k = N; k < N + 3; k++) { h.nptnr[k] = -2; h.ctype[k] = -2; }
+  CalEnt pad;
+  pad.t = 1e300; pad.ptnr = -1; pad.type = -1;
+  h.cal.assign(cal_stride, pad);
+  for (int k = 0; k < N; k++) h.cal[k].t = q.interval_max + 1e-10;  // main.F90:212
+  h.cal[N].t = 1000000000.0;                       // ghost: drawn on the device when canon (main.F90:408-416)
+  h.cal[N + 1].t = q.interval;                     // main.F90:421
+  h.cal[N + 2].t = 3.3 / (std::sqrt(q.setemp)) + 5;  // main.F90:423
+  for (int k = N; k < N + 3; k++) { h.cal[k].ptnr = -2; h.cal[k].type = -2; }
 }
 
 }  // namespace dmd

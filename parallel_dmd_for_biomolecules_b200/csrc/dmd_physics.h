@@ -68,13 +68,11 @@ DMD_DEV double core_sigsq(const Ctx& c, int code, int idi, int idj) {
 // One pair-time prediction = the dispatch of events.f:30-48 + core.f / bond.f / sqwel.f / nc_sqwel.f /
 // sqshlder.f.  `a` is the lower-index bead (event owner), `bonded` = (bptnr(a) == b).  Leaves tij/type
 // untouched when the pair has no event (the Fortran leaves tij at its 1e9 preset).
-DMD_DEV void pair_time(const Ctx& c, int code, const BeadRec& a, const BeadRec& b, uint32_t meta_a, bool bonded,
-                       double tfalse, double& tij, int& type) {
-  const Geom g = pair_geom(a, b, tfalse);
-  const double bij = g.bij;
-  const double rijsq = g.rx * g.rx + g.ry * g.ry + g.rz * g.rz;
-  const double vijsq = g.vx * g.vx + g.vy * g.vy + g.vz * g.vz;
-  const int idi = a.ident, idj = b.ident;
+// The predictors only use bij, |r|^2 and |v|^2, which are bitwise identical for (a,b) and (b,a) (negation is
+// exact), so the caller may form the geometry in either order; idi/idj/meta_a/bonded refer to the lower-index
+// bead first, as in the Fortran call core(i,j,...).
+DMD_DEV void pair_time_core(const Ctx& c, int code, double bij, double rijsq, double vijsq, int idi, int idj,
+                            uint32_t meta_a, bool bonded, double& tij, int& type) {
   if (code <= 3 || (code >= 17 && code <= 26)) {  // core.f:14-40
     if (bij < 0.0) {
       double sigsq = core_sigsq(c, code, idi, idj);
@@ -210,6 +208,14 @@ DMD_DEV void pair_time(const Ctx& c, int code, const BeadRec& a, const BeadRec& 
   }
 }
 
+DMD_DEV void pair_time(const Ctx& c, int code, const BeadRec& a, const BeadRec& b, uint32_t meta_a, bool bonded,
+                       double tfalse, double& tij, int& type) {
+  const Geom g = pair_geom(a, b, tfalse);
+  const double rijsq = g.rx * g.rx + g.ry * g.ry + g.rz * g.rz;
+  const double vijsq = g.vx * g.vx + g.vy * g.vy + g.vz * g.vz;
+  pair_time_core(c, code, g.bij, rijsq, vijsq, a.ident, b.ident, meta_a, bonded, tij, type);
+}
+
 // distance between two beads at the current false time (repuls_check.f:32-42)
 DMD_DEV double pair_dist(const BeadRec& a, const BeadRec& b, double tfalse) {
   Geom g = pair_geom(a, b, tfalse);
@@ -302,6 +308,46 @@ DMD_DEV int event_dynamics(const Ctx& c, int ct, int code, BeadRec& a, BeadRec& 
     b.x = b.x - sgn * (bumpdist * rxij);
     b.y = b.y - sgn * (bumpdist * ryij);
     b.z = b.z - sgn * (bumpdist * rzij);
+  }
+  const double delvx = ratio * rxij, delvy = ratio * ryij, delvz = ratio * rzij;  // eventdyn.f:366-381
+  a.vx = a.vx - delvx / bmi;
+  b.vx = b.vx + delvx / bmj;
+  a.vy = a.vy - delvy / bmi;
+  b.vy = b.vy + delvy / bmj;
+  a.vz = a.vz - delvz / bmi;
+  b.vz = b.vz + delvz / bmj;
+  a.x = a.x + delvx * tfalse / bmi;
+  a.y = a.y + delvy * tfalse / bmi;
+  a.z = a.z + delvz * tfalse / bmi;
+  b.x = b.x - delvx * tfalse / bmj;
+  b.y = b.y - delvy * tfalse / bmj;
+  b.z = b.z - delvz * tfalse / bmj;
+  return ct;
+}
+
+// the > 99 % case of eventdyn.f: hard-core (1) and bond (2, 3) events -- no bump, no type change.
+// Same arithmetic as event_dynamics(); kept separate so the hot loop stays small.
+DMD_DEV int event_dynamics_hot(const Ctx& c, int ct, int code, BeadRec& a, BeadRec& b, uint32_t meta_a, bool bonded,
+                               double tfalse) {
+  const Geom g = pair_geom(a, b, tfalse);
+  const double rxij = g.rx, ryij = g.ry, rzij = g.rz, bij = g.bij;
+  const int idi = a.ident, idj = b.ident;
+  const double bmi = c.sys->bmass[idi], bmj = c.sys->bmass[idj];
+  const double rmass = 2 * bmi * bmj / (bmi + bmj);
+  double ratio;
+  if (ct == 1) {
+    double sigsq;
+    if (code == 15) {
+      double f = c.sys->ev_param1[15];
+      sigsq = bonded ? c.tab->sigma_sq[tix(idi, idj)] * (f * f) : c.tab->sigma_sq[tix(idi, idj)];
+    } else {
+      sigsq = core_sigsq(c, code, idi, idj);
+    }
+    ratio = rmass * bij / sigsq;
+  } else {
+    double blmin, blmax;
+    bond_limits(c, code, meta_a, blmin, blmax);
+    ratio = ct == 2 ? rmass * bij / (blmin * blmin) : rmass * bij / (blmax * blmax);
   }
   const double delvx = ratio * rxij, delvy = ratio * ryij, delvz = ratio * rzij;  // eventdyn.f:366-381
   a.vx = a.vx - delvx / bmi;

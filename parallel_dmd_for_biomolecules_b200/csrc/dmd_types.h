@@ -108,6 +108,16 @@ constexpr int DMD_E_CAL_EMPTY = 2;  // calendar has no finite entry
 constexpr int DMD_E_NEG_TIME = 3;   // tij < -1e-10 (events.f:59-73 debugging guard)
 constexpr int DMD_E_GRID = 4;       // bead outside the cell grid
 
+// one calendar entry: tim(k), nptnr(k), coltype(k) of header.f:20-22,47 side by side so that popping the
+// minimum delivers the whole event in one access.  type: low 8 bits coltype (as int8), bits 8-15 the static
+// ev_code class of the (owner, partner) pair.
+struct alignas(16) CalEnt {
+  double t;
+  int32_t ptnr;  // 0-based partner, -1 none, -2 pseudo-event
+  int32_t type;
+};
+static_assert(sizeof(CalEnt) == 16, "CalEnt must be 16 bytes");
+
 struct EventLogRec {  // == dmdb_event
   double t;
   int32_t i, j, type, evcode;
@@ -128,9 +138,7 @@ struct DevArrays {
   const int32_t* chain;   // N (global chain index)
   // per replica
   BeadRec* rec;           // N
-  double* tim;            // N+3 (padded to ngroups*32)
-  int32_t* nptnr;         // N+3, 0-based partner or -1
-  int8_t* ctype;          // N+3
+  CalEnt* cal;            // N+3 entries padded to ngroups*32 (padding t = 1e300)
   int32_t* er34;          // 2N: extra_repuls(k,3), extra_repuls(k,4), 0-based or -1
   uint32_t* up;           // N*cap
   uint32_t* dn;           // N*cap
@@ -145,7 +153,7 @@ struct DevArrays {
   EventLogRec* log;       // log_cap
   OutRec* out;            // out_cap
   int32_t n_replicas;
-  int32_t tim_stride;     // ngroups*32
+  int32_t cal_stride;     // ngroups*32
 };
 
 }  // namespace dmd

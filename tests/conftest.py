@@ -1,0 +1,74 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from parallel_dmd_for_biomolecules_b200 import fileio, genconfig, tables  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SEQ_A = "GVAYVGSKTKEGVVHGVATVAE"  # recovered from genconfig/checks/identity.out
+HOSTTRACE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_trace", "libdmdb_hosttrace.so")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def tab():
+    return tables.load_default_tables()
+
+
+@pytest.fixture(scope="session")
+def system_a():
+    """The reference's shipped snapshot: 8 x 22-mer, N=672, L=110 A, T*=0.5."""
+    topo = tables.Topology([tables.Species.from_sequence(SEQ_A, 4), tables.Species.from_sequence(SEQ_A, 4)])
+    sv = fileio.sv_from_files(os.path.join(GOLDEN, "systemA_run0000.config"), os.path.join(GOLDEN, "systemA_run0000.lastvel"))
+    return topo, sv, 110.0
+
+
+@pytest.fixture(scope="session")
+def system_b(tab):
+    """BASELINE config 2: 48 x KLVFFAE, N=1344, L=158.54 A."""
+    topo, sv = genconfig.system_b(tab, 0.18, seed=1)
+    return topo, sv, 158.54
+
+
+@pytest.fixture(scope="session")
+def hosttrace_lib():
+    import __graft_entry__ as g
+    g.build()
+    return HOSTTRACE
+
+
+def compare_engines(ora, dev, replica=0, n_events=0, time_rtol=1e-12):
+    """The parity surface of BASELINE.json's north_star: bit-exact cells / neighbour sets / next-event partner and
+    type, event times within 1e-12 relative, identical committed-event sequence."""
+    assert np.array_equal(ora.cells(), dev.cells(replica)), "cell assignment"
+    for down in (False, True):
+        a, b = ora.nbors(down), dev.nbors(replica, down)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), "neighbour lists (down=%s)" % down
+    ta, na, ca = ora.calendar()
+    tb, nb, cb = dev.calendar(replica)
+    assert np.array_equal(na, nb), "next-event partner"
+    assert np.array_equal(ca, cb), "next-event type"
+    np.testing.assert_allclose(tb, ta, rtol=time_rtol, atol=0)
+    if n_events:
+        ora.run(n_events)
+        dev.run(n_events)
+        la, lb = ora.event_log(), dev.event_log(replica)
+        assert len(la) == len(lb) == n_events
+        for f in ("i", "j", "type", "evcode"):
+            bad = np.nonzero(la[f] != lb[f])[0]
+            assert bad.size == 0, "event sequence differs in %s at event %d: %s vs %s" % (f, bad[0], la[bad[0]], lb[bad[0]])
+        np.testing.assert_allclose(lb["t"], la["t"], rtol=time_rtol, atol=1e-300)
+        sa, sb = ora.state(), dev.state(replica)
+        np.testing.assert_allclose(sb["sv"], sa["sv"], rtol=1e-12, atol=1e-15)
+        for f in ("bptnr", "identity", "extra_repuls"):
+            assert np.array_equal(sa[f], sb[f]), f
+        assert sa["coll"] == sb["coll"]

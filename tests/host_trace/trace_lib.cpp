@@ -37,13 +37,14 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
   } else {
     for (int rid = r0; rid < r0 + nrep; rid++) {
       Rep r;
-      rep_bind(r, d, d.tables, rid);
+      int32_t cq[CQ_CAP];
+      rep_bind(r, d, d.tables, cq, rid);
       switch (op) {
         case 0:
           if (d.sys->canon) {
             double tgho = 0.0;
             while (tgho < 1e-18 || tgho == 1.0) tgho = rng_uniform(r.seed, r.ctr);
-            r.tim[r.N] = -1.0 * dmd_log(tgho) * r.avegtime * .0000001;
+            r.cal[r.N].t = -1.0 * dmd_log(tgho) * r.avegtime * .0000001;
           }
           nbor(r);
           predict_all(r);
