@@ -26,6 +26,9 @@
 namespace dmd {
 
 constexpr int WARPS_PER_CTA = 4;
+#ifndef DMD_MIN_CTAS
+#define DMD_MIN_CTAS 4  // 4 CTAs x 4 warps per SM at <= 128 registers per thread
+#endif
 
 __device__ __forceinline__ const PairTables* stage_tables(const DevArrays& d, PairTables* smem) {
   const double* src = reinterpret_cast<const double*>(d.tables);
@@ -45,7 +48,7 @@ __device__ __forceinline__ int replica_of_warp(int r0, int nrep) {
   return w < nrep ? r0 + w : -1;
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_event_loop_kernel(DevArrays d, int r0, int nrep, long long n_events) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, DMD_MIN_CTAS) dmd_event_loop_kernel(DevArrays d, int r0, int nrep, long long n_events) {
   __shared__ PairTables stab;
   const PairTables* tab = stage_tables(d, &stab);
   int rid = replica_of_warp(r0, nrep);

@@ -121,13 +121,7 @@ DMD_DEV void group_min_update(Rep& r, int g) {
     double x = r.cal[g * 32 + q].t;
     if (x < v) v = x;
   }
-#if DMD_W > 1
-#pragma unroll
-  for (int m = DMD_W / 2; m >= 1; m >>= 1) {
-    double ov = Warp::shfl_xor(v, m);
-    if (ov < v) v = ov;
-  }
-#endif
+  v = warp_min(v);
   if (Warp::lane() == 0) r.tmin1[g] = v;
 }
 
@@ -140,36 +134,58 @@ DMD_DEV void mark_dirty(Rep& r, int g) {  // g warp-uniform
   }
 }
 
+DMD_DEV int pop_lowest_bit(uint64_t& m) {
+#if defined(DMD_HOST_TRACE)
+  int g = __builtin_ctzll(m);
+#else
+  int g = __ffsll((long long)m) - 1;
+#endif
+  m &= m - 1;
+  return g;
+}
+
 DMD_DEV void flush_dirty(Rep& r) {
   Warp::sync();
-  while (r.dirty0) {
-#if defined(DMD_HOST_TRACE)
-    int g = __builtin_ctzll(r.dirty0);
-#else
-    int g = __ffsll((long long)r.dirty0) - 1;
-#endif
-    r.dirty0 &= r.dirty0 - 1;
-    group_min_update(r, g);
+#if DMD_W > 1
+  while (r.dirty0) {  // two groups per round so that their loads overlap
+    const int g0 = pop_lowest_bit(r.dirty0);
+    const int g1 = r.dirty0 ? pop_lowest_bit(r.dirty0) : -1;
+    double x0 = r.cal[g0 * 32 + Warp::lane()].t;
+    double x1 = g1 >= 0 ? r.cal[g1 * 32 + Warp::lane()].t : 0.0;
+    x0 = warp_min(x0);
+    if (g1 >= 0) x1 = warp_min(x1);
+    if (Warp::lane() == 0) {
+      r.tmin1[g0] = x0;
+      if (g1 >= 0) r.tmin1[g1] = x1;
+    }
   }
-  while (r.dirty1) {
-#if defined(DMD_HOST_TRACE)
-    int g = __builtin_ctzll(r.dirty1);
 #else
-    int g = __ffsll((long long)r.dirty1) - 1;
+  while (r.dirty0) group_min_update(r, pop_lowest_bit(r.dirty0));
 #endif
-    r.dirty1 &= r.dirty1 - 1;
-    group_min_update(r, 64 + g);
-  }
+  while (r.dirty1) group_min_update(r, 64 + pop_lowest_bit(r.dirty1));
   Warp::sync();
 }
 
 // every lane may have changed the entry of a different bead l (l < 0: none): record the groups uniformly
 DMD_DEV void mark_dirty_lanes(Rep& r, int l) {
-  unsigned m = Warp::ballot(l >= 0);
-  while (m) {
-    int src = dmd_ffs(m) - 1;
-    m &= m - 1;
-    mark_dirty(r, Warp::shfl(l, src) >> 5);
+  const int g = l >> 5;  // negative when l < 0
+  unsigned a0 = (g >= 0 && g < 32) ? 1u << g : 0u;
+  unsigned a1 = (g >= 32 && g < 64) ? 1u << (g - 32) : 0u;
+  a0 = warp_or(a0);
+  a1 = warp_or(a1);
+  r.dirty0 |= (uint64_t)a0 | ((uint64_t)a1 << 32);
+  if (r.G > 64) {  // larger systems (uniform branch)
+    unsigned b0 = (g >= 64 && g < 96) ? 1u << (g - 64) : 0u;
+    unsigned b1 = (g >= 96 && g < 128) ? 1u << (g - 96) : 0u;
+    b0 = warp_or(b0);
+    b1 = warp_or(b1);
+    r.dirty1 |= (uint64_t)b0 | ((uint64_t)b1 << 32);
+    unsigned m = Warp::ballot(g >= 128);
+    while (m) {
+      int src = dmd_ffs(m) - 1;
+      m &= m - 1;
+      mark_dirty(r, Warp::shfl(g, src));
+    }
   }
 }
 
@@ -232,6 +248,16 @@ DMD_DEV int sc_of(int packed) { return (packed >> 8) & 0xff; }
 // Lanes of the last two ranges that need a cascade push their bead on the queue r.cq.
 // ---------------------------------------------------------------------------------------------------------
 DMD_DEV void predict_pass(Rep& r, int a, bool with_down, int skip, int& cqn) {
+  // level-1 loads, all independent: the record of a, its list lengths, and (speculatively, before the lengths
+  // are known) the first 32 entries of both lists -- one entry per lane
+  const size_t lbase = (size_t)a * r.cap;
+#if DMD_W > 1
+  uint32_t eu0 = 0, ed0 = 0;
+  if (Warp::lane() < r.cap) {
+    eu0 = r.up[lbase + Warp::lane()];
+    if (with_down) ed0 = r.dn[lbase + Warp::lane()];
+  }
+#endif
   const BeadRec ra = r.rec[a];
   const uint32_t ma = r.c.meta[a];
   const int nu = r.nup[a];
@@ -245,35 +271,52 @@ DMD_DEV void predict_pass(Rep& r, int a, bool with_down, int skip, int& cqn) {
   for (int base = 0; base < total; base += DMD_W) {
     const int p = base + Warp::lane();
     int b = -1, sc = 1;  // the other bead of the pair and the pair's static class
-    bool full = p < nF;
+    const bool full = p < nF;
+    const int q = p - nF;  // index into the down list
+#if DMD_W > 1
+    const uint32_t edq = Warp::shfl((int)ed0, q & 31);
+#endif
     if (p < nu) {
-      uint32_t e = r.up[(size_t)a * r.cap + p];
+#if DMD_W > 1
+      uint32_t e = base == 0 ? eu0 : r.up[lbase + p];
+#else
+      uint32_t e = r.up[lbase + p];
+#endif
       b = (int)(e & NB_MASK);
       sc = (int)(e >> NB_SHIFT);
     } else if (p < nF) {
       int k = p - nu;
       b = k == 0 ? ra.er1 : (k == 1 ? ra.er2 : er3);
       if (b <= a) b = -1;  // events.f:77
-    } else if (p < nF + nd) {
-      uint32_t e = r.dn[(size_t)a * r.cap + (p - nF)];
+    } else if (q < nd) {
+#if DMD_W > 1
+      uint32_t e = q < 32 ? edq : r.dn[lbase + q];
+#else
+      uint32_t e = r.dn[lbase + q];
+#endif
       b = (int)(e & NB_MASK);
       sc = (int)(e >> NB_SHIFT);
       if (b == skip) b = -1;  // partial_events.f:136
     } else if (p < total) {
-      int k = p - nF - nd;
+      int k = q - nd;
       b = k == 0 ? ra.er1 : (k == 1 ? ra.er2 : er3);
       if (!(b >= 0 && b < a)) b = -1;  // partial_events.f:100,166
     }
     bool need_full = false;
     int changed = -1;
     if (b >= 0) {
+      // level-2 loads, all depending on b only
+      const BeadRec rb = r.rec[b];
       CalEnt eb;
       eb.t = 0.0; eb.ptnr = -1; eb.type = -1;
-      if (!full) eb = r.cal[b];
+      uint32_t mlo = ma;
+      if (!full) {
+        eb = r.cal[b];
+        mlo = r.c.meta[b];
+      }
       if (!full && eb.ptnr == a) {
         need_full = true;  // l's next event was with a: full re-prediction of l (cascade)
       } else {
-        const BeadRec rb = r.rec[b];
         const int code = overlay_code(sc, a, ra, b, rb);
         double tij = T_NONE;
         int type = -1;
@@ -282,7 +325,6 @@ DMD_DEV void predict_pass(Rep& r, int a, bool with_down, int skip, int& cqn) {
           const double rijsq = g.rx * g.rx + g.ry * g.ry + g.rz * g.rz;
           const double vijsq = g.vx * g.vx + g.vy * g.vy + g.vz * g.vz;
           const int idlo = full ? ra.ident : rb.ident, idhi = full ? rb.ident : ra.ident;
-          const uint32_t mlo = full ? ma : r.c.meta[b];
           const bool bonded = full ? ra.bptnr == b : rb.bptnr == a;
           pair_time_core(r.c, code, g.bij, rijsq, vijsq, idlo, idhi, mlo, bonded, tij, type);
         }

@@ -71,140 +71,100 @@ DMD_DEV double core_sigsq(const Ctx& c, int code, int idi, int idj) {
 // The predictors only use bij, |r|^2 and |v|^2, which are bitwise identical for (a,b) and (b,a) (negation is
 // exact), so the caller may form the geometry in either order; idi/idj/meta_a/bonded refer to the lower-index
 // bead first, as in the Fortran call core(i,j,...).
+//
+// All five Fortran predictors are the same computation with different radii and type labels:
+//   d1 = b^2 - v^2 (r^2 - R1^2)   inner radius R1: hard core (core.f:34), bond minimum (bond.f:46)
+//   d2 = b^2 - v^2 (r^2 - R2^2)   outer radius R2: bond maximum (bond.f:53), well (sqwel.f:41), shoulder
+//   t  = (-b -/+ sqrt(d)) / v^2,  or the cancellation-free -(r^2-R2^2)/(sqrt(d2)+b) for a receding bond (bond.f:63)
+// so the lanes of a warp (which hold pairs of different classes) select radii / root / type with predicates and
+// execute ONE sqrt and ONE division instead of diverging through five routines.  Every selected expression is
+// exactly the one the Fortran evaluates for that case.
 DMD_DEV void pair_time_core(const Ctx& c, int code, double bij, double rijsq, double vijsq, int idi, int idj,
                             uint32_t meta_a, bool bonded, double& tij, int& type) {
-  if (code <= 3 || (code >= 17 && code <= 26)) {  // core.f:14-40
-    if (bij < 0.0) {
-      double sigsq = core_sigsq(c, code, idi, idj);
-      double discr = bij * bij - vijsq * (rijsq - sigsq);
-      if (discr > 0.0) {
-        tij = (-bij - dmd_sqrt(discr)) / vijsq;
-        type = 1;
-      }
-    }
-  } else if (code <= 12) {  // bond.f:27-126
+  double R1sq, R2sq = 0.0;
+  int t_inner = 1, t_leave = 0, t_enter = 0;
+  int cls;                 // 0 core only, 1 bond, 2 well-like
+  int inside_force = 0;    // +1 treat as inside the well, -1 treat as outside
+  if (code <= 3 || (code >= 17 && code <= 26)) {  // core.f
+    cls = 0;
+    R1sq = core_sigsq(c, code, idi, idj);
+  } else if (code <= 12) {  // bond.f
+    cls = 1;
     double blmin, blmax;
     bond_limits(c, code, meta_a, blmin, blmax);
-    if (bij < 0.0) {
-      double discr1 = bij * bij - vijsq * (rijsq - blmin * blmin);
-      if (discr1 > 0.0) {
-        tij = (-bij - dmd_sqrt(discr1)) / vijsq;
-        type = 2;
-      } else {
-        double discr2 = bij * bij - vijsq * (rijsq - blmax * blmax);
-        if (discr2 > 0.0) {
-          tij = (-bij + dmd_sqrt(discr2)) / vijsq;
-          type = 3;
-        }
+    R1sq = blmin * blmin;
+    R2sq = blmax * blmax;
+    t_inner = 2;
+  } else {
+    cls = 2;
+    const double sig = c.tab->sigma_sq[tix(idi, idj)];
+    R1sq = sig;
+    if (code == 16) {  // sqwel.f
+      R2sq = c.tab->welldia_sq[tix(idi, idj)];
+      t_leave = 8;
+      t_enter = 4;
+    } else if (code == 15) {  // nc_sqwel.f
+      R2sq = c.tab->welldia_sq[tix(idi, idj)];
+      if (idi + idj == 5) {  // free N and free C
+        t_leave = 16;
+        t_enter = 7;
+      } else if (bonded) {  // bound to each other: core at the 1.05*(2.24 A) factor, exit 8, no inside test
+        const double f = c.sys->ev_param1[15];
+        R1sq = sig * f * f;
+        t_leave = 8;
+        inside_force = 1;
+      } else {  // not eligible: hard wall at the well diameter
+        t_enter = 9;
+        inside_force = -1;
       }
-    } else {
-      double discr2 = bij * bij - vijsq * (rijsq - blmax * blmax);
-      if (discr2 > 0.0) {
-        tij = -(rijsq - blmax * blmax) / (dmd_sqrt(discr2) + bij);
-        type = 3;
-      }
+    } else {  // sqshlder.f
+      R2sq = c.tab->shlddia_sq[tix(idi, idj)];
+      t_leave = 10;
+      t_enter = 12;
     }
-  } else if (code == 16) {  // sqwel.f:15-64
-    double diff = rijsq - c.tab->welldia_sq[tix(idi, idj)];
-    if (bij < 0.0) {
-      if (diff < 0.0) {
-        double corediscr = bij * bij - vijsq * (rijsq - c.tab->sigma_sq[tix(idi, idj)]);
-        if (corediscr > 0.0) {
-          tij = (-bij - dmd_sqrt(corediscr)) / vijsq;
-          type = 1;
-        } else {
-          double welldiscr = bij * bij - vijsq * diff;
-          tij = (-bij + dmd_sqrt(welldiscr)) / vijsq;
-          type = 8;
-        }
-      } else {
-        double welldiscr = bij * bij - vijsq * diff;
-        if (welldiscr > 0.0) {
-          tij = (-bij - dmd_sqrt(welldiscr)) / vijsq;
-          type = 4;
-        }
-      }
-    } else if (diff < 0.0) {
-      double welldiscr = bij * bij - vijsq * diff;
-      tij = (-bij + dmd_sqrt(welldiscr)) / vijsq;
-      type = 8;
-    }
-  } else if (code == 15) {  // nc_sqwel.f:19-122
-    double diff = rijsq - c.tab->welldia_sq[tix(idi, idj)];
-    if (idi + idj == 5) {
-      if (bij < 0.0) {
-        if (diff < 0.0) {
-          double corediscr = bij * bij - vijsq * (rijsq - c.tab->sigma_sq[tix(idi, idj)]);
-          if (corediscr > 0.0) {
-            tij = (-bij - dmd_sqrt(corediscr)) / vijsq;
-            type = 1;
-          } else {
-            double welldiscr = bij * bij - vijsq * diff;
-            tij = (-bij + dmd_sqrt(welldiscr)) / vijsq;
-            type = 16;
-          }
-        } else {
-          double welldiscr = bij * bij - vijsq * diff;
-          if (welldiscr > 0.0) {
-            tij = (-bij - dmd_sqrt(welldiscr)) / vijsq;
-            type = 7;
-          }
-        }
-      } else if (diff < 0.0) {
-        double welldiscr = bij * bij - vijsq * diff;
-        tij = (-bij + dmd_sqrt(welldiscr)) / vijsq;
-        type = 16;
-      }
-    } else if (bonded) {
-      if (bij < 0.0) {
-        double f = c.sys->ev_param1[15];
-        double fac_sigsq = c.tab->sigma_sq[tix(idi, idj)] * f * f;
-        double fac_cored = bij * bij - vijsq * (rijsq - fac_sigsq);
-        if (fac_cored > 0.0) {
-          tij = (-bij - dmd_sqrt(fac_cored)) / vijsq;
-          type = 1;
-        } else {
-          double welldiscr = bij * bij - vijsq * diff;
-          tij = (-bij + dmd_sqrt(welldiscr)) / vijsq;
-          type = 8;
-        }
-      } else {
-        double welldiscr = bij * bij - vijsq * diff;
-        tij = (-bij + dmd_sqrt(welldiscr)) / vijsq;
-        type = 8;
-      }
-    } else if (bij < 0.0) {
-      double welldiscr = bij * bij - vijsq * diff;
-      if (welldiscr > 0.0) {
-        tij = (-bij - dmd_sqrt(welldiscr)) / vijsq;
-        type = 9;
-      }
-    }
-  } else {  // code >= 40: sqshlder.f:15-63
-    double diff = rijsq - c.tab->shlddia_sq[tix(idi, idj)];
-    if (bij < 0.0) {
-      if (diff < 0.0) {
-        double corediscr = bij * bij - vijsq * (rijsq - c.tab->sigma_sq[tix(idi, idj)]);
-        if (corediscr > 0.0) {
-          tij = (-bij - dmd_sqrt(corediscr)) / vijsq;
-          type = 1;
-        } else {
-          double shlddiscr = bij * bij - vijsq * diff;
-          tij = (-bij + dmd_sqrt(shlddiscr)) / vijsq;
-          type = 10;
-        }
-      } else {
-        double shlddiscr = bij * bij - vijsq * diff;
-        if (shlddiscr > 0.0) {
-          tij = (-bij - dmd_sqrt(shlddiscr)) / vijsq;
-          type = 12;
-        }
-      }
-    } else if (diff < 0.0) {
-      double shlddiscr = bij * bij - vijsq * diff;
-      tij = (-bij + dmd_sqrt(shlddiscr)) / vijsq;
-      type = 10;
-    }
+  }
+  const bool approaching = bij < 0.0;
+  const double diff2 = rijsq - R2sq;
+  const bool inside = inside_force > 0 || (inside_force == 0 && diff2 < 0.0);
+  const double bb = bij * bij;
+  const double d1 = bb - vijsq * (rijsq - R1sq);
+  const double d2 = bb - vijsq * diff2;
+  bool valid, alt = false;
+  double d, sgn;
+  int ty;
+  if (approaching && d1 > 0.0 && (cls != 2 || inside)) {  // inner root: core hit / bond minimum
+    valid = true;
+    d = d1;
+    sgn = -1.0;
+    ty = t_inner;
+  } else if (cls == 0) {
+    valid = false;
+    d = 1.0;
+    sgn = 1.0;
+    ty = -1;
+  } else if (cls == 1) {  // bond maximum
+    valid = d2 > 0.0;
+    d = d2;
+    sgn = 1.0;
+    ty = 3;
+    alt = !approaching;
+  } else if (approaching && !inside) {  // capture / enter (or wall) at R2 from outside
+    valid = d2 > 0.0;
+    d = d2;
+    sgn = -1.0;
+    ty = t_enter;
+  } else {  // leave the well / shoulder at R2 from inside
+    valid = inside;
+    d = d2;
+    sgn = 1.0;
+    ty = t_leave;
+  }
+  if (valid) {
+    const double sq = dmd_sqrt(d);
+    const double num = alt ? -diff2 : (-bij + sgn * sq);
+    const double den = alt ? (sq + bij) : vijsq;
+    tij = num / den;
+    type = ty;
   }
 }
 

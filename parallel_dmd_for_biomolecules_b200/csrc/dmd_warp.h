@@ -76,19 +76,56 @@ DMD_DEV unsigned dmd_lo(double d) { return (unsigned)__double2loint(d); }
 
 namespace dmd {
 
-// (value, key) lexicographic arg-min over the warp: smallest value, ties -> smallest key.  All lanes get it.
+// fp64 -> uint64 whose unsigned order equals the numeric order (no NaNs on this path)
+DMD_DEV void ord_split(double v, unsigned& hi, unsigned& lo) {
+  int h = dmd_hi(v);
+  unsigned l = dmd_lo(v);
+  if (h < 0) {
+    hi = ~(unsigned)h;
+    lo = ~l;
+  } else {
+    hi = (unsigned)h | 0x80000000u;
+    lo = l;
+  }
+}
+DMD_DEV double ord_join(unsigned hi, unsigned lo) {
+  if (hi & 0x80000000u) return dmd_hi_lo((int)(hi & 0x7fffffffu), lo);
+  return dmd_hi_lo((int)~hi, ~lo);
+}
+
+// (value, key) lexicographic arg-min over the warp: smallest value, ties -> smallest key (key >= 0).
+// All lanes get the result.  Three REDUX.MIN instructions on the device instead of a 5-round shuffle tree.
 DMD_DEV void warp_argmin(double& v, int& key) {
 #if DMD_W > 1
-#pragma unroll
-  for (int m = DMD_W / 2; m >= 1; m >>= 1) {
-    double ov = Warp::shfl_xor(v, m);
-    int ok = Warp::shfl_xor(key, m);
-    if (ov < v || (ov == v && ok < key)) {
-      v = ov;
-      key = ok;
-    }
-  }
+  unsigned hi, lo;
+  ord_split(v, hi, lo);
+  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+  const bool c1 = hi == mhi;
+  const unsigned mlo = __reduce_min_sync(0xffffffffu, c1 ? lo : 0xffffffffu);
+  const bool c2 = c1 && lo == mlo;
+  const unsigned mkey = __reduce_min_sync(0xffffffffu, c2 ? (unsigned)key : 0xffffffffu);
+  v = ord_join(mhi, mlo);
+  key = (int)mkey;
 #endif
+}
+
+// minimum value only
+DMD_DEV double warp_min(double v) {
+#if DMD_W > 1
+  unsigned hi, lo;
+  ord_split(v, hi, lo);
+  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+  v = ord_join(mhi, mlo);
+#endif
+  return v;
+}
+
+DMD_DEV unsigned warp_or(unsigned x) {
+#if DMD_W > 1
+  x = __reduce_or_sync(0xffffffffu, x);
+#endif
+  return x;
 }
 
 DMD_DEV double warp_max(double v) {
@@ -104,8 +141,7 @@ DMD_DEV double warp_max(double v) {
 
 DMD_DEV int warp_sum(int v) {
 #if DMD_W > 1
-#pragma unroll
-  for (int m = DMD_W / 2; m >= 1; m >>= 1) v += Warp::shfl_xor(v, m);
+  v = __reduce_add_sync(0xffffffffu, v);
 #endif
   return v;
 }
