@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native PRIME20 DMD engine.
+
+Metric (BASELINE.json): DMD collision events/s per B200 (every processed calendar event, counted like the
+reference's `coll`, main.F90:639).  Workload at N=1: BASELINE config 2 -- the 48-peptide Abeta16-22 (KLVFFAE)
+PRIME20 box, N = 1344 beads, L = 158.54 A, T* = 0.18, Andersen thermostat on (-Dcanon) -- as an ensemble of R
+independent replicas resident on one GPU (one warp per replica).  N>1: the same per-GPU workload on every GPU
+(weak scaling) plus one replica-exchange collective (NCCL all-gather of (E_pot, T*)) per step.
+
+A "step" = every replica advances `--events` calendar events (one launch of the persistent event-loop kernel).
+
+  value : whole-job events/s with state resident in HBM (device time of the event-loop kernel, CUDA events on the
+          library's stream, max over ranks)
+  e2e   : the same metric through the C ABI with HOST buffers inside the timed region: dmdb_set_state_all (H2D of
+          every replica's restart state from pinned memory, run start: nbor + events) -> dmdb_run ->
+          dmdb_sync_positions -> dmdb_get_state_all + dmdb_potential_energies (D2H)
+  --impl reference : the reference's CPU implementation of the path.  The Fortran cannot be built in this image
+          (no Fortran compiler, Intel IFPORT, MPI), so this times the C++ oracle port of it on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "DMD collision events/sec per B200"
+UNIT = "events/s"
+WORKLOAD = "config2: 48 x Abeta16-22 (KLVFFAE) PRIME20 box, N=1344 beads, L=158.54 A, T*=0.18, canon"
+TSTAR, BOXL = 0.18, 158.54
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--replicas", type=int, default=2368, help="replicas per GPU (148 SMs x 16 warps)")
+    ap.add_argument("--events", type=int, default=20000, help="calendar events per replica per step")
+    ap.add_argument("--ref-events", type=int, default=400000, help="events per host thread per step (--impl reference)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(n_beads, d_events, d_pair, d_ghost, d_visits):
+    """a committed pair event moves 2*64 (records) + 2*48 + 2*16 (results) + 84 B per neighbour-list
+    entry visited (4 B entry + 64 B partner record + 16 B calendar entry); an interval pseudo-event (advance_sync)
+    moves 48N + 24N + 16(N+3).  List rebuilds are NOT counted (conservative)."""
+    interval = max(d_events - d_pair - d_ghost, 0)
+    return d_pair * 256 + d_visits * 84 + d_ghost * (64 + 84 * 10) + interval * (72 * n_beads + 16 * (n_beads + 3))
+
+
+def cpu_baseline_sample(tab, topo, sv, seconds_target=12.0):
+    """the oracle (port of the reference's serial algorithm) on ONE host core, bounded sample of the same workload"""
+    from oracle.binding import OracleDMD
+    from parallel_dmd_for_biomolecules_b200 import tables
+    o = OracleDMD(tables.make_params(boxl=BOXL, tstar=TSTAR, canon=True), topo, tab)
+    o.set_state(sv)
+    o.run(100000)
+    n, sec = 0, 0.0
+    while sec < seconds_target:
+        sec += o.run(500000)
+        n += 500000
+    return {"value": n / sec, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d events of one replica of the workload after 1e5 warm-up events, C++ oracle (g++ -O2 "
+                      "-ffp-contract=off), %.1f s" % (n, sec)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the oracle port on every host core (one independent replica per thread)."""
+    if rank != 0:
+        return
+    from oracle.binding import OracleDMD
+    from parallel_dmd_for_biomolecules_b200 import genconfig, tables
+    tab = tables.load_default_tables()
+    topo, sv = genconfig.system_b(tab, TSTAR, seed=1)
+    T = os.cpu_count() or 1
+    reps = []
+    for k in range(T):
+        o = OracleDMD(tables.make_params(boxl=BOXL, tstar=TSTAR, canon=True, seed=1058472402 + k), topo, tab)
+        o.set_state(sv)
+        reps.append(o)
+
+    def step():
+        th = [threading.Thread(target=o.run, args=(args.ref_events,)) for o in reps]  # ctypes releases the GIL
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = T * args.ref_events * args.steps / dt
+    sample = "%d host threads x %d events per step, one replica of the workload per thread" % (T, args.ref_events)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "the Fortran reference cannot be compiled in this image; this is its C++ "
+                   "oracle port (oracle/), serial semantics, one trajectory per host thread"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": T, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+
+    from parallel_dmd_for_biomolecules_b200 import genconfig, replica_exchange, tables
+    from parallel_dmd_for_biomolecules_b200.dmd import DMD
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    tab = tables.load_default_tables()
+    topo, sv = genconfig.system_b(tab, TSTAR, seed=1)
+    N, R, E = topo.n_beads, args.replicas, args.events
+    p = tables.make_params(boxl=BOXL, tstar=TSTAR, canon=True, n_replicas=R, device=local_rank, seed=1058472402 + 100003 * rank)
+    d = DMD(p, topo, tab)
+    d.set_state(sv)
+
+    def step(k):
+        st = d.run(E)
+        if world > 1:  # the replica-set exchange; equal temperatures -> decisions are no-ops
+            replica_exchange.exchange_step(d, k, seed=4242, device=dev)
+        return st.device_ms
+
+    for k in range(args.warmup):
+        step(k)
+    s0 = d.stats()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for k in range(args.steps):
+        dev_ms += step(args.warmup + k)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    s1 = d.stats()
+    # ---- e2e through the C ABI with host buffers (pinned), copies inside the timed region
+    d.sync_positions()
+    host_sv = torch.empty((R, N, 6), dtype=torch.float64, pin_memory=True).numpy()
+    host_bp = torch.empty((R, N), dtype=torch.int32, pin_memory=True).numpy()
+    d.get_state_all(host_sv, host_bp)
+
+    def e2e_step():
+        d.set_state_all(host_sv, host_bp)
+        d.run(E)
+        d.sync_positions()
+        d.get_state_all(host_sv, host_bp)
+        return d.potential_energies()[0]
+
+    e2e_step()
+    barrier()
+    t1 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        epot = e2e_step()
+    barrier()
+    e2e_wall = time.perf_counter() - t1
+    cal_stride = ((N + 3 + 31) // 32) * 32
+    h2d = R * (N * 64 + 2 * N * 4 + 3 * N * 8 + cal_stride * 16 + 512)  # rec, er34, oldr, cal, scalars (library copies)
+    d2h = R * N * 64 + R * 64 + R * 512  # records, energy records, scalars
+    # ---- reduce over ranks
+    vals = torch.tensor([dev_ms, wall, e2e_wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_max, e2e_wall_max = [float(x) for x in vals.cpu()]
+    d_events = s1.events - s0.events
+    d_pair = s1.pair_events - s0.pair_events
+    d_ghost = s1.ghosts - s0.ghosts
+    d_visits = s1.nbr_visits - s0.nbr_visits
+    total_events = world * R * E * args.steps
+    value = total_events / (dev_ms_max * 1e-3)
+    peak, peak_src = measured_peak()
+    abytes = algorithmic_bytes(N, d_events, d_pair, d_ghost, d_visits)
+    achieved = abytes / (dev_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "event_loop_traffic.json")) as f:
+            traffic = json.load(f)["dram_bytes_per_event"] * R * E
+    except Exception:
+        pass
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "replicas_per_gpu": R, "beads_per_replica": N, "events_per_replica_per_step": E,
+                       "parallelism": "one warp per replica, %d replicas per GPU, %d GPU(s)%s" % (
+                           R, world, ", NCCL all-gather replica exchange per step" if world > 1 else ""),
+                       "l2": "no flush needed: resident working set per GPU %.1f GB >> 126 MB L2" % (R * N * 1100 / 1e9),
+                       "event_count_convention": "all calendar events incl. ghost/interval pseudo-events (main.F90:639)",
+                       "pair_event_fraction": d_pair / max(d_events, 1),
+                       "mean_list_entries_visited_per_event": d_visits / max(d_events, 1),
+                       "single_trajectory_events_per_s": value / (world * R),
+                       "wall_ms_per_step": 1e3 * wall_max / args.steps},
+            "clocks": clocks,
+            "e2e": {"value": world * R * E * e2e_steps / e2e_wall_max, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "path": "dmdb_set_state_all(pinned host sv,bptnr) -> dmdb_run -> dmdb_sync_positions -> "
+                            "dmdb_get_state_all + dmdb_potential_energies"},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "dmd_event_loop_kernel",
+                         "algorithmic_bytes_per_launch": abytes / args.steps,
+                         "note": "latency/issue-bound gather workload: see DESIGN.md 'Roofline'"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_sample(tab, topo, sv)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

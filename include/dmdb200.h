@@ -126,6 +126,10 @@ int dmdb_num_cells(const dmdb_handle* h); /* num_cell per dimension, main.F90:39
  * rebuilds identity +4, extra_repuls and the 40/50 overlay geometrically (main.F90:249-321), sets the
  * pseudo-event times (main.F90:408-423), then runs nbor() and events().  replica = -1 loads every replica. */
 int dmdb_set_state(dmdb_handle* h, int replica, const double* sv, const int32_t* bptnr);
+/* Same for every replica at once from distinct configurations: sv_all is n_replicas x (6 x N), bptnr_all
+ * n_replicas x N or NULL.  One host->device copy per array (this is the end-to-end path bench.py times). */
+int dmdb_set_state_all(dmdb_handle* h, const double* sv_all, const int32_t* bptnr_all);
+int dmdb_get_state_all(dmdb_handle* h, double* sv_all, int32_t* bptnr_all);
 /* Temperature change on resident state (what a new `./dmd < temp_0xx` run does through a restart). */
 int dmdb_set_temperature(dmdb_handle* h, int replica, double tstar);
 
@@ -157,6 +161,10 @@ int dmdb_get_replica_stats(dmdb_handle* h, int replica, dmdb_stats* s);
  * The collective itself is done by the host language binding over NCCL (torch.distributed) -- see
  * INTEGRATION.md; the library computes the local potential energies and applies temperature swaps. */
 int dmdb_potential_energies(dmdb_handle* h, double* epot /* n_replicas */, double* tstar /* n_replicas */);
+/* Applies the outcome of an exchange: replicas whose entry differs from their current T* have their velocities
+ * rescaled by sqrt(T_new/T_old), their time constants reset (main.F90:143-156) and lists + calendar rebuilt, all
+ * on the device; H-bond state is kept.  Entries <= 0 leave the replica untouched. */
+int dmdb_apply_temperatures(dmdb_handle* h, const double* tstar_new /* n_replicas */);
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,9 @@ class OracleDMD:
     def set_temperature(self, tstar):
         self._chk(self._l.dmdo_set_temperature(self._h, C.c_double(tstar)))
 
+    def retemp(self, tstar):
+        self._chk(self._l.dmdo_retemp(self._h, C.c_double(tstar)))
+
     def nbor(self):
         self._chk(self._l.dmdo_nbor(self._h))
 

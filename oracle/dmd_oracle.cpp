@@ -1330,6 +1330,44 @@ void Oracle::set_temperature(double tstar) {
   set_state(s.data(), bp.data());
 }
 
+// Replica-exchange temperature change on resident state.  NOT in the reference: defined here and
+// in the engine identically -- true positions, velocities scaled by sqrt(T_new/T_old), time constants of
+// main.F90:143-156 reset, lists and calendar rebuilt, H-bond state kept.
+void Oracle::retemp(double tstar_new) {
+  const int N = noptotal;
+  const double tf = tfalse;
+  const double setemp_new = tstar_new * 12.0;
+  const double scale = std::sqrt(setemp_new / setemp);
+  t = t + tf;
+  for (int k = 1; k <= N; k++) {
+    double x = S(1, k) + S(4, k) * tf, y = S(2, k) + S(5, k) * tf, z = S(3, k) + S(6, k) * tf;
+    x = x - dnint(x); y = y - dnint(y); z = z - dnint(z);
+    S(1, k) = x; S(2, k) = y; S(3, k) = z;
+    S(4, k) = S(4, k) * scale; S(5, k) = S(5, k) * scale; S(6, k) = S(6, k) * scale;
+    old_rx[k] = x; old_ry[k] = y; old_rz[k] = z;
+  }
+  tfalse = 0.0; old_tfalse = 0.0;
+  setemp = setemp_new;
+  t_fact = 0.00005; n_forced = 150.0;
+  interval = t_fact / std::sqrt(setemp);
+  interval_max = n_forced * interval;
+  sortsize = interval_max / (double)numbin;
+  avegtime = 0.00005 / std::sqrt(setemp);
+  tbin_off = 0.0; nbin = 1;
+  double tg = 1000000000.0;
+  if (canon) {
+    double tgho = 0.0;
+    while (tgho < 1e-18 || tgho == 1.0) tgho = rng_uniform();
+    tg = -1.0 * fdlibm_log(tgho) * avegtime;
+  }
+  tim[N + 1] = tg;
+  tim[N + 2] = interval;
+  tim[N + 3] = 3.3 / (std::sqrt(setemp)) + 5;
+  nbor();
+  for (int k = 1; k <= N; k++) { tim[k] = interval_max + ltstep; coltype[k] = -1; nptnr[k] = -1; }
+  events();
+}
+
 // main.F90:1288-1297
 void Oracle::sync_positions() {
   for (int k = 1; k <= noptotal; k++) {

@@ -49,6 +49,7 @@ class Oracle {
   // ---- restart path: inputinfo.f:76-101 + main.F90:205-321, 347-424
   void set_state(const double* sv6xN, const int* bptnr_or_null);
   void set_temperature(double tstar);
+  void retemp(double tstar_new);  // replica-exchange temperature change on resident state (new functionality)
 
   // ---- reference operator API
   void nbor_setup();                                   // nbor_setup.f:13-118

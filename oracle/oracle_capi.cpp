@@ -34,6 +34,7 @@ int dmdo_num_cells(void* h) { return ((Oracle*)h)->num_cell; }
 
 int dmdo_set_state(void* h, const double* sv, const int32_t* bptnr) { GUARD(((Oracle*)h)->set_state(sv, bptnr)) }
 int dmdo_set_temperature(void* h, double tstar) { GUARD(((Oracle*)h)->set_temperature(tstar)) }
+int dmdo_retemp(void* h, double tstar) { GUARD(((Oracle*)h)->retemp(tstar)) }
 int dmdo_nbor(void* h) { GUARD(((Oracle*)h)->nbor()) }
 int dmdo_predict_all(void* h) {
   Oracle* o = (Oracle*)h;

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/dmdb200.h"
@@ -16,7 +17,7 @@
 #include "dmd_types.h"
 
 namespace dmd {
-enum Op { OP_START = 0, OP_NBOR, OP_PREDICT_ALL, OP_RUN, OP_SYNC_POS, OP_ENERGY, OP_EVCODE };
+enum Op { OP_START = 0, OP_NBOR, OP_PREDICT_ALL, OP_RUN, OP_SYNC_POS, OP_ENERGY, OP_EVCODE, OP_RETEMP };
 }
 
 static thread_local std::string g_create_error;
@@ -29,6 +30,7 @@ struct dmdb_handle {
   std::vector<char> loaded;   // per replica: dmdb_set_state done
   dmd::OutRec* eout = nullptr;   // device: n_replicas
   int32_t* pair_buf = nullptr;   // device scratch for dmdb_get_evcode
+  double* temp_buf = nullptr;    // device: n_replicas new temperatures (dmdb_apply_temperatures)
   size_t pair_cap = 0;
   std::string err;
   double last_ms = 0;
@@ -148,6 +150,7 @@ int dmdb_create(const dmdb_params* p, const dmdb_topology* topo, const dmdb_tabl
     d.log = dalloc<dmd::EventLogRec>(h.get(), R * (size_t)std::max(s.log_cap, 1));
     d.out = dalloc<dmd::OutRec>(h.get(), R * (size_t)s.out_cap);
     h->eout = dalloc<dmd::OutRec>(h.get(), R);
+    h->temp_buf = dalloc<double>(h.get(), R);
     be::zero(d.nup, R * N * 2);
     be::zero(d.ndn, R * N * 2);
     h->tstar.assign(R, p->tstar);
@@ -174,19 +177,64 @@ const char* dmdb_last_error(const dmdb_handle* h) { return h ? h->err.c_str() : 
 int dmdb_num_beads(const dmdb_handle* h) { return h ? h->model.sys.N : -1; }
 int dmdb_num_cells(const dmdb_handle* h) { return h ? h->model.sys.num_cell : -1; }
 
-static int upload_replica(dmdb_handle* h, int r, const double* sv, const int32_t* bptnr) {
+// Build the run-start state of replicas [r0, r1) on host threads and upload each array with ONE copy.
+// sv_stride / bp_stride = 0 gives every replica the same configuration (different RNG streams).
+static void upload_replicas(dmdb_handle* h, int r0, int r1, const double* sv, size_t sv_stride, const int32_t* bptnr,
+                            size_t bp_stride) {
   const dmd::SysConst& s = h->model.sys;
-  const size_t N = (size_t)s.N, rr = (size_t)r;
-  dmd::HostReplicaInit init;
-  dmd::build_replica_init(h->model, sv, bptnr, h->tstar[r], h->model.params.seed + (uint64_t)r, h->d.cal_stride, init);
+  const size_t N = (size_t)s.N, n = (size_t)(r1 - r0), cs = (size_t)h->d.cal_stride;
+  std::vector<dmd::BeadRec> rec(n * N);
+  std::vector<int32_t> er34(n * 2 * N);
+  std::vector<double> oldr(n * 3 * N);
+  std::vector<dmd::CalEnt> cal(n * cs);
+  std::vector<dmd::RepScalars> scal(n);
+  std::string err;
+  auto work = [&](size_t k0, size_t k1) {
+    try {
+      dmd::HostReplicaInit init;
+      for (size_t k = k0; k < k1; k++) {
+        const int r = r0 + (int)k;
+        const bool same = sv_stride == 0 && k > k0;
+        if (!same)
+          dmd::build_replica_init(h->model, sv + k * sv_stride, bptnr ? bptnr + k * bp_stride : nullptr, h->tstar[r],
+                                  h->model.params.seed + (uint64_t)r, h->d.cal_stride, init);
+        if (same) {  // identical configuration: only the temperature-dependent scalars and the seed differ
+          dmd::HostReplicaInit tmp;
+          tmp.scal = init.scal;
+          dmd::init_scalars(tmp.scal, h->tstar[r], h->model.params.seed + (uint64_t)r);
+          init.scal = tmp.scal;
+          dmd::init_calendar(s, init.scal, h->d.cal_stride, init.cal);
+        }
+        std::copy(init.rec.begin(), init.rec.end(), rec.begin() + k * N);
+        std::copy(init.er34.begin(), init.er34.end(), er34.begin() + k * 2 * N);
+        std::copy(init.oldr.begin(), init.oldr.end(), oldr.begin() + k * 3 * N);
+        std::copy(init.cal.begin(), init.cal.end(), cal.begin() + k * cs);
+        scal[k] = init.scal;
+      }
+    } catch (const std::exception& e) {
+      err = e.what();
+    }
+  };
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  if (nt > 32) nt = 32;
+  if (n < 2 * (size_t)nt) nt = 1;
+  if (nt == 1) {
+    work(0, n);
+  } else {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++) th.emplace_back(work, n * t / nt, n * (t + 1) / nt);
+    for (auto& x : th) x.join();
+  }
+  if (!err.empty()) throw std::runtime_error(err);
   dmd::DevArrays& d = h->d;
-  be::h2d(d.rec + rr * N, init.rec.data(), N * sizeof(dmd::BeadRec));
-  be::h2d(d.er34 + rr * 2 * N, init.er34.data(), 2 * N * 4);
-  be::h2d(d.oldr + rr * 3 * N, init.oldr.data(), 3 * N * 8);
-  be::h2d(d.cal + rr * d.cal_stride, init.cal.data(), (size_t)d.cal_stride * sizeof(dmd::CalEnt));
-  be::h2d(d.scal + rr, &init.scal, sizeof(dmd::RepScalars));
-  h->loaded[r] = 1;
-  return 0;
+  const size_t rr = (size_t)r0;
+  be::h2d(d.rec + rr * N, rec.data(), n * N * sizeof(dmd::BeadRec));
+  be::h2d(d.er34 + rr * 2 * N, er34.data(), n * 2 * N * 4);
+  be::h2d(d.oldr + rr * 3 * N, oldr.data(), n * 3 * N * 8);
+  be::h2d(d.cal + rr * cs, cal.data(), n * cs * sizeof(dmd::CalEnt));
+  be::h2d(d.scal + rr, scal.data(), n * sizeof(dmd::RepScalars));
+  for (int r = r0; r < r1; r++) h->loaded[r] = 1;
 }
 
 int dmdb_set_state(dmdb_handle* h, int replica, const double* sv, const int32_t* bptnr) {
@@ -197,8 +245,20 @@ int dmdb_set_state(dmdb_handle* h, int replica, const double* sv, const int32_t*
   }
   try {
     const int r0 = replica < 0 ? 0 : replica, r1 = replica < 0 ? h->d.n_replicas : replica + 1;
-    for (int r = r0; r < r1; r++) upload_replica(h, r, sv, bptnr);
+    upload_replicas(h, r0, r1, sv, 0, bptnr, 0);
     be::run_op(h->d, dmd::OP_START, r0, r1 - r0, 0, nullptr, nullptr, &h->last_ms, &h->last_launches);
+  } catch (const std::exception& e) {
+    return fail(h, DMDB_ERR_ARG, e.what());
+  }
+  return check_device_errors(h);
+}
+
+int dmdb_set_state_all(dmdb_handle* h, const double* sv_all, const int32_t* bptnr_all) {
+  if (!h || !sv_all) return fail(h, DMDB_ERR_ARG, "null argument");
+  try {
+    const size_t N = (size_t)h->model.sys.N;
+    upload_replicas(h, 0, h->d.n_replicas, sv_all, 6 * N, bptnr_all, N);
+    be::run_op(h->d, dmd::OP_START, 0, h->d.n_replicas, 0, nullptr, nullptr, &h->last_ms, &h->last_launches);
   } catch (const std::exception& e) {
     return fail(h, DMDB_ERR_ARG, e.what());
   }
@@ -225,7 +285,7 @@ int dmdb_set_temperature(dmdb_handle* h, int replica, double tstar) {
       int rc = dmdb_get_state(h, r, sv.data(), bp.data(), nullptr, nullptr, nullptr, nullptr, nullptr);
       if (rc) return rc;
       h->tstar[r] = tstar;
-      upload_replica(h, r, sv.data(), bp.data());
+      upload_replicas(h, r, r + 1, sv.data(), 0, bp.data(), 0);
     }
     be::run_op(h->d, dmd::OP_START, r0, r1 - r0, 0, nullptr, nullptr, &h->last_ms, &h->last_launches);
   })
@@ -357,6 +417,47 @@ int dmdb_get_state(dmdb_handle* h, int replica, double* sv, int32_t* bptnr, int3
     }
   })
   return DMDB_OK;
+}
+
+int dmdb_get_state_all(dmdb_handle* h, double* sv_all, int32_t* bptnr_all) {
+  int rc = all_loaded(h);
+  if (rc) return rc;
+  const size_t N = (size_t)h->model.sys.N, R = (size_t)h->d.n_replicas;
+  DMDB_TRY(h, {
+    std::vector<dmd::BeadRec> rec(R * N);
+    be::d2h(rec.data(), h->d.rec, R * N * sizeof(dmd::BeadRec));
+    for (size_t k = 0; k < R * N; k++) {
+      const dmd::BeadRec& b = rec[k];
+      if (sv_all) {
+        double* o = sv_all + 6 * k;
+        o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.vx; o[4] = b.vy; o[5] = b.vz;
+      }
+      if (bptnr_all) bptnr_all[k] = b.bptnr + 1;
+    }
+  })
+  return DMDB_OK;
+}
+
+int dmdb_apply_temperatures(dmdb_handle* h, const double* tstar_new) {
+  int rc = all_loaded(h);
+  if (rc) return rc;
+  if (!tstar_new) return fail(h, DMDB_ERR_ARG, "null argument");
+  const int R = h->d.n_replicas;
+  DMDB_TRY(h, {
+    std::vector<double> tn(R);
+    bool any = false;
+    for (int r = 0; r < R; r++) {
+      tn[r] = (tstar_new[r] > 0 && tstar_new[r] != h->tstar[r]) ? tstar_new[r] : 0.0;
+      any = any || tn[r] > 0;
+    }
+    if (any) {
+      be::h2d(h->temp_buf, tn.data(), sizeof(double) * R);
+      be::run_op(h->d, dmd::OP_RETEMP, 0, R, 0, (int32_t*)h->temp_buf, nullptr, &h->last_ms, &h->last_launches);
+      for (int r = 0; r < R; r++)
+        if (tn[r] > 0) h->tstar[r] = tn[r];
+    }
+  })
+  return check_device_errors(h);
 }
 
 int dmdb_get_evcode(dmdb_handle* h, int replica, int n_pairs, const int32_t* i, const int32_t* j, int32_t* code) {

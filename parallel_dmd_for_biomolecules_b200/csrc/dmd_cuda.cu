@@ -7,6 +7,7 @@
 //   dmd_predict_all_kernel   events.f             (dmdb_predict_all)
 //   dmd_sync_positions_kernel main.F90:1288-1295
 //   dmd_energy_kernel        energy.f
+//   dmd_retemp_kernel        replica-exchange temperature change on resident state (new functionality)
 //   dmd_evcode_kernel        ev_code(i,j) read-back for the parity tests
 // There is no CPU fallback: be::init fails when no CUDA device is present.
 #include <cuda_runtime.h>
@@ -118,6 +119,19 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_energy_kernel(DevArray
   if (Warp::lane() == 0) eout[rid] = o;
 }
 
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_retemp_kernel(DevArrays d, int r0, int nrep, const double* tstar_new) {
+  __shared__ PairTables stab;
+  const PairTables* tab = stage_tables(d, &stab);
+  int rid = replica_of_warp(r0, nrep);
+  if (rid < 0) return;
+  const double tn = tstar_new[rid];
+  if (!(tn > 0.0)) return;  // <= 0: leave this replica untouched
+  Rep r;
+  rep_bind(r, d, tab, warp_queue(), rid);
+  retemp(r, tn);
+  rep_save(r);
+}
+
 __global__ void dmd_evcode_kernel(DevArrays d, int rid, int n_pairs, int32_t* buf) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_pairs) return;
@@ -193,6 +207,7 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
     case 4: dmd_sync_positions_kernel<<<grid, block, 0, g_stream>>>(d, r0, nrep); break;
     case 5: dmd_energy_kernel<<<grid, block, 0, g_stream>>>(d, r0, nrep, eout); break;
     case 6: dmd_evcode_kernel<<<((int)arg + 127) / 128, 128, 0, g_stream>>>(d, r0, (int)arg, ibuf); break;
+    case 7: dmd_retemp_kernel<<<grid, block, 0, g_stream>>>(d, r0, nrep, (const double*)ibuf); break;
     default: throw std::runtime_error("unknown device op");
   }
   CUDA_OK(cudaGetLastError());

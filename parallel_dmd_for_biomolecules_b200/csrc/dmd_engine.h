@@ -1026,6 +1026,49 @@ DMD_DEV void run_events(Rep& r, int64_t n_events) {
   flush_dirty(r);
 }
 
+// Replica-exchange temperature change on resident state (new functionality): advance to true
+// positions, rescale velocities by sqrt(T_new/T_old), reset the time constants of main.F90:143-156 for the new
+// temperature and rebuild lists + calendar.  H-bond state (bptnr, identity, extra_repuls, overlay) is kept.
+DMD_DEV void retemp(Rep& r, double tstar_new) {
+  const int N = r.N;
+  const double tf = r.tfalse;
+  const double setemp_new = tstar_new * 12.0;
+  const double scale = dmd_sqrt(setemp_new / r.setemp);
+  r.t = r.t + tf;
+  Warp::sync();
+  for (int k = Warp::lane(); k < N; k += DMD_W) {
+    BeadRec* p = &r.rec[k];
+    double x = p->x + p->vx * tf, y = p->y + p->vy * tf, z = p->z + p->vz * tf;
+    x = x - dmd_round(x); y = y - dmd_round(y); z = z - dmd_round(z);
+    p->x = x; p->y = y; p->z = z;
+    p->vx = p->vx * scale; p->vy = p->vy * scale; p->vz = p->vz * scale;
+    r.oldr[3 * k] = x; r.oldr[3 * k + 1] = y; r.oldr[3 * k + 2] = z;
+  }
+  r.tfalse = 0.0;
+  r.old_tfalse = 0.0;
+  r.setemp = setemp_new;
+  r.t_fact = 0.00005;
+  r.n_forced = 150.0;
+  r.interval = r.t_fact / dmd_sqrt(r.setemp);
+  r.interval_max = r.n_forced * r.interval;
+  r.avegtime = 0.00005 / dmd_sqrt(r.setemp);
+  double tg = 1000000000.0;
+  if (r.c.sys->canon) {
+    double tgho = 0.0;
+    while (tgho < 1e-18 || tgho == 1.0) tgho = rng_uniform(r.seed, r.ctr);
+    tg = -1.0 * dmd_log(tgho) * r.avegtime;
+  }
+  Warp::sync();
+  if (Warp::lane() == 0) {
+    r.cal[N].t = tg;
+    r.cal[N + 1].t = r.interval;
+    r.cal[N + 2].t = 3.3 / (dmd_sqrt(r.setemp)) + 5;
+  }
+  Warp::sync();
+  nbor(r);
+  predict_all(r);
+}
+
 // main.F90:1288-1295 (then the state must be re-initialised by the host before running on)
 DMD_DEV void sync_positions(Rep& r) {
   for (int k = Warp::lane(); k < r.N; k += DMD_W) {

@@ -21,6 +21,7 @@ struct HostModel {
   std::vector<uint32_t> meta;
   std::vector<int32_t> chain;
   std::vector<uint8_t> id0;
+  std::vector<int32_t> nc_beads;  // indices of the N and C beads (ascending): the only H-bond capable ones
   dmdb_params params;
 };
 
@@ -192,6 +193,7 @@ inline void build_model(const dmdb_params& p, const dmdb_topology& topo, const d
         m.meta[bead] = meta_pack(cls, res, topo.hp[sp][l] == 1, id, sp, proex, l);
         m.chain[bead] = chain;
         m.id0[bead] = (uint8_t)id;
+        if (cls == 1 || cls == 2) m.nc_beads.push_back(bead);
       }
   }
   // ---- nbor_setup.f:13-118 (first chain of each species against itself and each other)
@@ -244,6 +246,31 @@ inline void build_model(const dmdb_params& p, const dmdb_topology& topo, const d
   s.half = boxl / 2.0;
 }
 
+// main.F90:127,143-156: time constants of a run at temperature tstar
+inline void init_scalars(RepScalars& q, double tstar, uint64_t seed) {
+  std::memset(&q, 0, sizeof(q));
+  q.setemp = tstar * 12.0;                       // main.F90:127
+  q.t_fact = 0.00005;                            // main.F90:144
+  q.n_forced = 150.0;
+  q.interval = q.t_fact / std::sqrt(q.setemp);
+  q.interval_max = q.n_forced * q.interval;
+  q.avegtime = 0.00005 / std::sqrt(q.setemp);    // main.F90:156
+  q.rng_seed = seed;
+}
+
+// main.F90:212-234, 408-423: every bead at interval_max + ltstep, pseudo-events armed
+inline void init_calendar(const SysConst& s, const RepScalars& q, int cal_stride, std::vector<CalEnt>& cal) {
+  const int N = s.N;
+  CalEnt pad;
+  pad.t = 1e300; pad.ptnr = -1; pad.type = -1;
+  cal.assign(cal_stride, pad);
+  for (int k = 0; k < N; k++) cal[k].t = q.interval_max + 1e-10;  // main.F90:212
+  cal[N].t = 1000000000.0;                       // ghost: drawn on the device when canon (main.F90:408-416)
+  cal[N + 1].t = q.interval;                     // main.F90:421
+  cal[N + 2].t = 3.3 / (std::sqrt(q.setemp)) + 5;  // main.F90:423
+  for (int k = N; k < N + 3; k++) { cal[k].ptnr = -2; cal[k].type = -2; }
+}
+
 inline void host_set_pair_code(std::vector<BeadRec>& rec, int a, int b, int code) {
   if (rec[a].er1 == b) rec[a].ov1 = (uint8_t)code;
   if (rec[a].er2 == b) rec[a].ov2 = (uint8_t)code;
@@ -291,19 +318,21 @@ inline void build_replica_init(const HostModel& m, const double* sv, const int32
     h.oldr[3 * (size_t)k] = x; h.oldr[3 * (size_t)k + 1] = y; h.oldr[3 * (size_t)k + 2] = z;
   }
   // main.F90:249-321, literal pair order (identity changes made on the way affect later tests)
-  for (int k = 0; k < N - 1; k++) {
-    const int cls_k = meta_cls(m.meta[k]);
-    if (cls_k != 1 && cls_k != 2) continue;  // only N / C beads can satisfy either test
-    for (int kj = k + 1; kj < N; kj++) {
+  // (only N / C beads can satisfy either test, so the literal k < k_j double loop is restricted to them)
+  const std::vector<int32_t>& nc = m.nc_beads;
+  for (size_t ik = 0; ik < nc.size(); ik++) {
+    const int k = nc[ik];
+    for (size_t ij = ik + 1; ij < nc.size(); ij++) {
+      const int kj = nc[ij];
       BeadRec& a = h.rec[k];
       BeadRec& b = h.rec[kj];
-      if (a.ident + b.ident == 5 &&
-          static_code(s, m.meta[k], m.chain[k], k, m.meta[kj], m.chain[kj], kj) == 15) {
+      if (a.ident + b.ident == 5) {
         double rx = a.x - b.x, ry = a.y - b.y, rz = a.z - b.z;
         rx = rx - std::round(rx); ry = ry - std::round(ry); rz = rz - std::round(rz);
         double rijsq = rx * rx + ry * ry + rz * rz;
         double diff = rijsq - m.tab.welldia_sq[(a.ident - 1) * 28 + (b.ident - 1)];
-        if (diff < 0.0 && !is_terminal_bead(s, m.meta[k]) && !is_terminal_bead(s, m.meta[kj])) {
+        if (diff < 0.0 && static_code(s, m.meta[k], m.chain[k], k, m.meta[kj], m.chain[kj], kj) == 15 &&
+            !is_terminal_bead(s, m.meta[k]) && !is_terminal_bead(s, m.meta[kj])) {
           if (a.ident == 1) host_repuls_add(m, h, k, kj);
           else host_repuls_add(m, h, kj, k);
         }
@@ -314,23 +343,8 @@ inline void build_replica_init(const HostModel& m, const double* sv, const int32
       }
     }
   }
-  RepScalars& q = h.scal;
-  std::memset(&q, 0, sizeof(q));
-  q.setemp = tstar * 12.0;                       // main.F90:127
-  q.t_fact = 0.00005;                            // main.F90:144
-  q.n_forced = 150.0;
-  q.interval = q.t_fact / std::sqrt(q.setemp);
-  q.interval_max = q.n_forced * q.interval;
-  q.avegtime = 0.00005 / std::sqrt(q.setemp);    // main.F90:156
-  q.rng_seed = seed;
-  CalEnt pad;
-  pad.t = 1e300; pad.ptnr = -1; pad.type = -1;
-  h.cal.assign(cal_stride, pad);
-  for (int k = 0; k < N; k++) h.cal[k].t = q.interval_max + 1e-10;  // main.F90:212
-  h.cal[N].t = 1000000000.0;                       // ghost: drawn on the device when canon (main.F90:408-416)
-  h.cal[N + 1].t = q.interval;                     // main.F90:421
-  h.cal[N + 2].t = 3.3 / (std::sqrt(q.setemp)) + 5;  // main.F90:423
-  for (int k = N; k < N + 3; k++) { h.cal[k].ptnr = -2; h.cal[k].type = -2; }
+  init_scalars(h.scal, tstar, seed);
+  init_calendar(s, h.scal, cal_stride, h.cal);
 }
 
 }  // namespace dmd

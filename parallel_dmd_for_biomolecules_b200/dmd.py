@@ -26,7 +26,8 @@ SYMBOLS = [
     "dmdb_create", "dmdb_destroy", "dmdb_last_error", "dmdb_num_beads", "dmdb_num_cells", "dmdb_set_state",
     "dmdb_set_temperature", "dmdb_nbor", "dmdb_predict_all", "dmdb_run", "dmdb_sync_positions", "dmdb_get_cells",
     "dmdb_get_nbors", "dmdb_get_calendar", "dmdb_get_state", "dmdb_get_evcode", "dmdb_energy_of",
-    "dmdb_get_event_log", "dmdb_get_replica_stats", "dmdb_potential_energies",
+    "dmdb_get_event_log", "dmdb_get_replica_stats", "dmdb_potential_energies", "dmdb_set_state_all",
+    "dmdb_get_state_all", "dmdb_apply_temperatures",
 ]
 
 
@@ -96,6 +97,30 @@ class DMD:
             raise ValueError(f"sv must have shape ({self.N}, 6) (Fortran sv(6,N))")
         bp = None if bptnr is None else np.ascontiguousarray(bptnr, dtype=np.int32)
         self._chk(self._l.dmdb_set_state(self._h, replica, _p(sv, C.c_double), None if bp is None else _p(bp, C.c_int32)))
+
+    def set_state_all(self, sv_all: np.ndarray, bptnr_all: Optional[np.ndarray] = None):
+        """distinct configuration per replica: sv_all (n_replicas, N, 6); one H2D copy per device array"""
+        if sv_all.dtype != np.float64 or not sv_all.flags.c_contiguous or sv_all.shape != (self.n_replicas, self.N, 6):
+            raise ValueError(f"sv_all must be C-contiguous float64 of shape ({self.n_replicas}, {self.N}, 6)")
+        bp = None if bptnr_all is None else np.ascontiguousarray(bptnr_all, dtype=np.int32)
+        self._chk(self._l.dmdb_set_state_all(self._h, _p(sv_all, C.c_double), None if bp is None else _p(bp, C.c_int32)))
+
+    def get_state_all(self, out: Optional[np.ndarray] = None, out_bptnr: Optional[np.ndarray] = None) -> np.ndarray:
+        """every replica's sv (and optionally bptnr) into caller-owned host buffers (may be pinned)"""
+        if out is None:
+            out = np.empty((self.n_replicas, self.N, 6))
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (self.n_replicas, self.N, 6)
+        if out_bptnr is not None:
+            assert out_bptnr.dtype == np.int32 and out_bptnr.flags.c_contiguous and out_bptnr.shape == (self.n_replicas, self.N)
+        self._chk(self._l.dmdb_get_state_all(self._h, _p(out, C.c_double),
+                                             None if out_bptnr is None else _p(out_bptnr, C.c_int32)))
+        return out
+
+    def apply_temperatures(self, tstar_new):
+        """replica-exchange outcome: per-replica new T* (entries equal to the current T* are left alone)"""
+        t = np.ascontiguousarray(tstar_new, dtype=np.float64)
+        assert t.shape == (self.n_replicas,)
+        self._chk(self._l.dmdb_apply_temperatures(self._h, _p(t, C.c_double)))
 
     def set_temperature(self, tstar: float, replica: int = -1):
         self._chk(self._l.dmdb_set_temperature(self._h, replica, C.c_double(tstar)))

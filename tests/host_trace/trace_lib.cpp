@@ -55,6 +55,7 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
         case 3: if (r.error == 0) run_events(r, arg); rep_save(r); break;
         case 4: sync_positions(r); break;
         case 5: { OutRec o; energy_of(r, o); eout[rid] = o; } break;
+        case 7: { double tn = ((const double*)ibuf)[rid]; if (tn > 0.0) { retemp(r, tn); rep_save(r); } } break;
         default: throw std::runtime_error("unknown op");
       }
     }

@@ -1,0 +1,150 @@
+"""`-m gpu` parity tests: libdmdb200.so (CUDA, sm_100a) through the C ABI against the CPU oracle on identical
+snapshots.  Bars (BASELINE.json north_star): cell / neighbour assignment and per-bead next-event partner and
+type bit-exact, event times within 1e-12 relative (they are in fact bit-equal), first 1e4+ committed events in
+sequence; at full size (thousands of replicas) size-independent properties: NVE energy conservation, no
+overlaps (checkover.f) and run-to-run determinism."""
+import numpy as np
+import pytest
+
+from conftest import compare_engines
+from oracle.binding import OracleDMD
+from parallel_dmd_for_biomolecules_b200 import genconfig, tables
+from parallel_dmd_for_biomolecules_b200.dmd import DMD, DMDError
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(p, topo, tab, sv, bptnr=None):
+    ora = OracleDMD(p, topo, tab)
+    ora.set_state(sv, bptnr)
+    dev = DMD(p, topo, tab)  # the product library; raises without a CUDA device
+    dev.set_state(sv, bptnr)
+    return ora, dev
+
+
+@pytest.mark.parametrize("which,canon,n_events", [("A", False, 20000), ("A", True, 50000), ("B", False, 20000), ("B", True, 100000)])
+def test_event_sequence_matches_oracle(tab, system_a, system_b, which, canon, n_events):
+    topo, sv, boxl = system_a if which == "A" else system_b
+    p = tables.make_params(boxl=boxl, tstar=0.5 if which == "A" else 0.18, canon=canon, n_replicas=5, log_capacity=n_events)
+    ora, dev = _pair(p, topo, tab, sv)
+    compare_engines(ora, dev, replica=0, n_events=n_events)
+    ea, eb = ora.energy(), dev.energy(0)
+    assert (ea.hb_ii, ea.hb_ij, ea.hb_alpha) == (eb.hb_ii, eb.hb_ij, eb.hb_alpha)
+    np.testing.assert_allclose([eb.ered, eb.tred, eb.ehh_ii, eb.ehh_ij], [ea.ered, ea.tred, ea.ehh_ii, ea.ehh_ij], rtol=1e-12, atol=1e-12)
+    sa, sb = ora.stats(), dev.stats(0)
+    assert list(sa.nevents) == list(sb.nevents)
+    assert (sa.ghosts, sa.updates, sa.forced_updates) == (sb.ghosts, sb.updates, sb.forced_updates)
+    if canon:  # replica 3 draws from another RNG stream: compare it with its own oracle
+        p3 = tables.make_params(boxl=boxl, tstar=0.5 if which == "A" else 0.18, canon=True, log_capacity=n_events, seed=p.seed + 3)
+        o3 = OracleDMD(p3, topo, tab)
+        o3.set_state(sv)
+        o3.run(n_events)
+        l3, d3 = o3.event_log(), dev.event_log(3)
+        assert np.array_equal(l3["i"], d3["i"]) and np.array_equal(l3["j"], d3["j"]) and np.array_equal(l3["type"], d3["type"])
+    else:  # NVE replicas started from the same snapshot are bit-identical
+        assert np.array_equal(dev.state(0)["sv"], dev.state(4)["sv"])
+
+
+def test_hbond_rich_trajectory_and_restart(tab):
+    topo, sv = genconfig.generate_box(["AAAAAAAAAAAA"], [8], 45.0, 0.10, tab, seed=1)
+    n = 600000
+    p = tables.make_params(boxl=45.0, tstar=0.10, canon=True, n_replicas=2, log_capacity=n, seed=11)
+    ora, dev = _pair(p, topo, tab, sv)
+    compare_engines(ora, dev, n_events=n)
+    st = ora.stats()
+    assert min(st.nevents[14], st.nevents[15], st.nevents[16], st.nevents[20], st.nevents[24], st.nevents[26]) > 0
+    ora.sync_positions()
+    s = ora.state()
+    assert (s["bptnr"] > 0).sum() >= 2
+    p2 = tables.make_params(boxl=45.0, tstar=0.10, canon=True, n_replicas=1, log_capacity=20000, seed=12)
+    ora2, dev2 = _pair(p2, topo, tab, s["sv"], bptnr=s["bptnr"])
+    assert np.array_equal(ora2.state()["identity"], dev2.state()["identity"])
+    assert np.array_equal(ora2.state()["extra_repuls"], dev2.state()["extra_repuls"])
+    compare_engines(ora2, dev2, n_events=20000)
+
+
+def test_static_evcode_function_equals_literal_matrix(tab):
+    for seqs, counts in ((["KLVFFAE", "GVAYVGSKTKEGVVHGVATVAE"], [3, 2]), (["APGLPVAEKG"], [4]), (["GGPKAG", "PAAPG"], [2, 3])):
+        topo = tables.Topology([tables.Species.from_sequence(s, c) for s, c in zip(seqs, counts)])
+        p = tables.make_params(boxl=200.0, tstar=0.3, canon=False)
+        rng = np.random.default_rng(0)
+        sv = np.concatenate([rng.random((topo.n_beads, 3)) - 0.5, rng.normal(size=(topo.n_beads, 3))], axis=1)
+        m = OracleDMD(p, topo, tab).evcode_matrix()
+        dev = DMD(p, topo, tab)
+        dev.set_state(sv)
+        N = topo.n_beads
+        ii, jj = np.meshgrid(np.arange(1, N + 1), np.arange(1, N + 1), indexing="ij")
+        mask = ii != jj
+        got = dev.evcode(ii[mask], jj[mask])
+        overlay = got >= 40
+        assert np.array_equal(got[~overlay], m[mask][~overlay])
+
+
+def test_retemp_and_distinct_states(tab, system_b):
+    topo, sv, boxl = system_b
+    p = tables.make_params(boxl=boxl, tstar=0.18, canon=True, n_replicas=3, log_capacity=40000)
+    ora, dev = _pair(p, topo, tab, sv)
+    ora.run(10000)
+    dev.run(10000)
+    ora.retemp(0.26)
+    dev.apply_temperatures([0.26, 0.18, 0.30])
+    compare_engines(ora, dev, replica=0, n_events=0)
+    ora.run(20000)
+    dev.run(20000)
+    la, lb = ora.event_log(), dev.event_log(0)
+    assert np.array_equal(la["i"], lb["i"]) and np.array_equal(la["type"], lb["type"]) and np.array_equal(la["t"], lb["t"])
+    # distinct configurations per replica through the batched upload
+    _, sv1 = genconfig.system_b(tab, 0.18, seed=6)
+    p2 = tables.make_params(boxl=boxl, tstar=0.18, canon=False, n_replicas=2, log_capacity=5000)
+    dev2 = DMD(p2, topo, tab)
+    dev2.set_state_all(np.ascontiguousarray(np.stack([sv, sv1])))
+    for r, s in ((0, sv), (1, sv1)):
+        o = OracleDMD(p2, topo, tab)
+        o.set_state(s)
+        compare_engines(o, dev2, replica=r, n_events=5000 if r == 1 else 0)
+
+
+def test_full_size_properties(tab, system_b):
+    """BASELINE config 2 at bench size: 2368 replicas of the 48-peptide box.  Size-independent properties:
+    NVE energy is conserved in every replica, every replica's final state passes checkover.f (sampled), identical
+    replicas stay bit-identical, and a second run of the same handle state is deterministic."""
+    topo, sv, boxl = system_b
+    R = 2368
+    p = tables.make_params(boxl=boxl, tstar=0.18, canon=False, n_replicas=R)
+    dev = DMD(p, topo, tab)
+    dev.set_state(sv)
+    e0 = dev.energy(0).ered
+    st = dev.run(20000)
+    assert st.events == R * 20000
+    ep, _ = dev.potential_energies()
+    out = dev.get_state_all()
+    assert np.array_equal(out[0], out[R - 1]) and np.array_equal(out[0], out[R // 2])
+    for r in (0, 777, R - 1):
+        assert abs(dev.energy(r).ered - e0) < 1e-6
+    o = OracleDMD(tables.make_params(boxl=boxl, tstar=0.18, canon=False), topo, tab)
+    dev.sync_positions()
+    o.set_state(dev.state(R - 1)["sv"], dev.state(R - 1)["bptnr"])
+    assert not o.checkover()[0]
+    # thermostatted ensemble: replicas decorrelate, temperature is held, no replica reports a device error
+    p = tables.make_params(boxl=boxl, tstar=0.18, canon=True, n_replicas=R)
+    dev = DMD(p, topo, tab)
+    dev.set_state(sv)
+    dev.run(30000)
+    tr = np.array([dev.energy(r).tred for r in range(0, R, 37)])
+    assert abs(tr.mean() - 2.16) < 0.05 and tr.std() > 1e-4
+    dev.sync_positions()
+    o.set_state(dev.state(5)["sv"], dev.state(5)["bptnr"])
+    assert not o.checkover()[0]
+
+
+def test_errors_are_reported_not_fatal(tab, system_b):
+    topo, sv, boxl = system_b
+    dev = DMD(tables.make_params(boxl=boxl, tstar=0.18, nbr_capacity=4), topo, tab)
+    with pytest.raises(DMDError) as e:
+        dev.set_state(sv)
+    assert e.value.code == 5
+    dev2 = DMD(tables.make_params(boxl=boxl, tstar=0.18), topo, tab)
+    with pytest.raises(DMDError):
+        dev2.run(10)  # no state loaded
+    with pytest.raises(ValueError):
+        dev2.set_state(sv[:10])
