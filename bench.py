@@ -237,9 +237,8 @@ def main():
         epot = e2e_step()
     barrier()
     e2e_wall = time.perf_counter() - t1
-    cal_stride = ((N + 3 + 31) // 32) * 32
-    h2d = R * (N * 64 + 2 * N * 4 + 3 * N * 8 + cal_stride * 16 + 512)  # rec, er34, oldr, cal, scalars (library copies)
-    d2h = R * N * 64 + R * 64 + R * 512  # records, energy records, scalars
+    h2d = R * (N * 48 + N * 4 + 8)  # raw sv + bptnr + temperatures; every derived array is built on the device
+    d2h = R * (N * 48 + N * 4) + R * 64 + 2 * R * 512  # sv + bptnr, energy records, per-replica scalars (error words)
     # ---- reduce over ranks
     vals = torch.tensor([dev_ms, wall, e2e_wall], dtype=torch.float64, device=dev)
     if world > 1:

@@ -80,7 +80,9 @@ typedef struct dmdb_params {
   int32_t device;       /* CUDA device ordinal */
   int32_t nbr_capacity; /* per-bead capacity of the up and of the down neighbour list (0 = default 64) */
   int32_t log_capacity; /* per-replica event-log ring capacity in events (0 = no log) */
-  int32_t reserved;
+  int32_t engine;       /* event-loop engine: 0 = automatic, 1 = one warp per replica (throughput: thousands of
+                           replicas), 2 = one CTA per replica with batched conservative commit (latency: a few
+                           trajectories; state resident in shared memory).  Results are bit-identical. */
   uint64_t seed;        /* replica r draws from the counter RNG stream seed + r (replaces Intel drandm) */
 } dmdb_params;
 
@@ -156,6 +158,11 @@ int dmdb_get_evcode(dmdb_handle* h, int replica, int n_pairs, const int32_t* i, 
 int dmdb_energy_of(dmdb_handle* h, int replica, dmdb_energy* e); /* = energy() */
 int dmdb_get_event_log(dmdb_handle* h, int replica, int64_t first, int64_t n, dmdb_event* out, int64_t* n_out);
 int dmdb_get_replica_stats(dmdb_handle* h, int replica, dmdb_stats* s);
+/* Batching statistics of the CTA-per-replica engine (summed over replicas when replica = -1): out[0] rounds,
+ * [1] events executed speculatively, [2] of those rolled back (main.F90:970-993 rule), [3] candidates dropped by a
+ * footprint conflict, [4] events processed serially at the head (H-bond events, pseudo-events), [5..7] reserved,
+ * [8..14] SM clock cycles spent in the phases scan / select+sort / claim / check / exec / commit / serial. */
+int dmdb_get_batch_stats(dmdb_handle* h, int replica, int64_t out[16]);
 
 /* Replica exchange (new functionality, no reference counterpart): gathers (E_pot, T*) of the local replicas.
  * The collective itself is done by the host language binding over NCCL (torch.distributed) -- see

@@ -17,7 +17,7 @@
 #include "dmd_types.h"
 
 namespace dmd {
-enum Op { OP_START = 0, OP_NBOR, OP_PREDICT_ALL, OP_RUN, OP_SYNC_POS, OP_ENERGY, OP_EVCODE, OP_RETEMP };
+enum Op { OP_START = 0, OP_NBOR, OP_PREDICT_ALL, OP_RUN, OP_SYNC_POS, OP_ENERGY, OP_EVCODE, OP_RETEMP, OP_RUN_BLOCK };
 }
 
 static thread_local std::string g_create_error;
@@ -30,7 +30,9 @@ struct dmdb_handle {
   std::vector<char> loaded;   // per replica: dmdb_set_state done
   dmd::OutRec* eout = nullptr;   // device: n_replicas
   int32_t* pair_buf = nullptr;   // device scratch for dmdb_get_evcode
-  double* temp_buf = nullptr;    // device: n_replicas new temperatures (dmdb_apply_temperatures)
+  double* temp_buf = nullptr;    // device: n_replicas temperatures (run start, dmdb_apply_temperatures)
+  double* stage_sv = nullptr;    // device staging: n_replicas x N x 6 raw sv (dmdb_set_state*, dmdb_get_state_all)
+  int32_t* stage_bp = nullptr;   // device staging: n_replicas x N bptnr
   size_t pair_cap = 0;
   std::string err;
   double last_ms = 0;
@@ -79,6 +81,7 @@ const char* device_error_text(int e) {
     case dmd::DMD_E_CAL_EMPTY: return "event calendar empty";
     case dmd::DMD_E_NEG_TIME: return "negative event time";
     case dmd::DMD_E_GRID: return "bead outside the cell grid";
+    case dmd::DMD_E_BAD_INPUT: return "bptnr entry out of range";
   }
   return "unknown device error";
 }
@@ -92,7 +95,8 @@ int check_device_errors(dmdb_handle* h) {
     if (sc[r].error) {
       char buf[256];
       snprintf(buf, sizeof buf, "replica %d: %s (info %d)", r, device_error_text(sc[r].error), sc[r].error_info);
-      int code = sc[r].error == dmd::DMD_E_NBR_CAP ? DMDB_ERR_CAPACITY : DMDB_ERR_PHYSICS;
+      int code = sc[r].error == dmd::DMD_E_NBR_CAP ? DMDB_ERR_CAPACITY
+                 : (sc[r].error == dmd::DMD_E_BAD_INPUT ? DMDB_ERR_ARG : DMDB_ERR_PHYSICS);
       return fail(h, code, buf);
     }
   return 0;
@@ -105,6 +109,7 @@ extern "C" {
 int dmdb_create(const dmdb_params* p, const dmdb_topology* topo, const dmdb_tables* tab, dmdb_handle** out) {
   if (!p || !topo || !tab || !out) return fail(nullptr, DMDB_ERR_ARG, "null argument");
   if (p->n_replicas < 1) return fail(nullptr, DMDB_ERR_ARG, "n_replicas must be >= 1");
+  if (p->engine < 0 || p->engine > 2) return fail(nullptr, DMDB_ERR_ARG, "engine must be 0 (auto), 1 (warp) or 2 (block)");
   std::string err;
   if (!be::init(p->device, err)) return fail(nullptr, DMDB_ERR_NO_DEVICE, err);
   std::unique_ptr<dmdb_handle> h(new dmdb_handle());
@@ -120,12 +125,24 @@ int dmdb_create(const dmdb_params* p, const dmdb_topology* topo, const dmdb_tabl
     std::memset(&d, 0, sizeof(d));
     d.n_replicas = (int)R;
     d.cal_stride = s.ngroups * 32;
+    d.n_beads = s.N;
     dmd::SysConst* dsys = dalloc<dmd::SysConst>(h.get(), 1);
     be::h2d(dsys, &s, sizeof(s));
     d.sys = dsys;
     dmd::PairTables* dtab = dalloc<dmd::PairTables>(h.get(), 1);
     be::h2d(dtab, &h->model.tab, sizeof(dmd::PairTables));
     d.tables = dtab;
+    dmd::HotConst* dhot = dalloc<dmd::HotConst>(h.get(), 1);
+    be::h2d(dhot, &h->model.hot, sizeof(dmd::HotConst));
+    d.hot = dhot;
+    double* dbl = dalloc<double>(h.get(), h->model.bl.size());
+    be::h2d(dbl, h->model.bl.data(), h->model.bl.size() * sizeof(double));
+    d.bl = dbl;
+    d.nres = h->model.hot.nres;
+    int32_t* dnc = dalloc<int32_t>(h.get(), h->model.nc_beads.size());
+    be::h2d(dnc, h->model.nc_beads.data(), h->model.nc_beads.size() * 4);
+    d.nc_beads = dnc;
+    d.n_nc = (int)h->model.nc_beads.size();
     uint32_t* dmeta = dalloc<uint32_t>(h.get(), N);
     be::h2d(dmeta, h->model.meta.data(), N * 4);
     d.meta = dmeta;
@@ -149,6 +166,8 @@ int dmdb_create(const dmdb_params* p, const dmdb_topology* topo, const dmdb_tabl
     d.scal = dalloc<dmd::RepScalars>(h.get(), R);
     d.log = dalloc<dmd::EventLogRec>(h.get(), R * (size_t)std::max(s.log_cap, 1));
     d.out = dalloc<dmd::OutRec>(h.get(), R * (size_t)s.out_cap);
+    d.blkstat = dalloc<long long>(h.get(), R * 16);
+    be::zero(d.blkstat, R * 16 * sizeof(long long));
     h->eout = dalloc<dmd::OutRec>(h.get(), R);
     h->temp_buf = dalloc<double>(h.get(), R);
     be::zero(d.nup, R * N * 2);
@@ -177,63 +196,23 @@ const char* dmdb_last_error(const dmdb_handle* h) { return h ? h->err.c_str() : 
 int dmdb_num_beads(const dmdb_handle* h) { return h ? h->model.sys.N : -1; }
 int dmdb_num_cells(const dmdb_handle* h) { return h ? h->model.sys.num_cell : -1; }
 
-// Build the run-start state of replicas [r0, r1) on host threads and upload each array with ONE copy.
-// sv_stride / bp_stride = 0 gives every replica the same configuration (different RNG streams).
+// Run start of replicas [r0, r1): ONE host->device copy of the raw sv (and bptnr) into staging, then the device
+// builds every per-replica array (init_replica in dmd_engine.h).  sv_stride / bp_stride = 0 gives every replica
+// the same configuration (different RNG streams).
 static void upload_replicas(dmdb_handle* h, int r0, int r1, const double* sv, size_t sv_stride, const int32_t* bptnr,
                             size_t bp_stride) {
   const dmd::SysConst& s = h->model.sys;
-  const size_t N = (size_t)s.N, n = (size_t)(r1 - r0), cs = (size_t)h->d.cal_stride;
-  std::vector<dmd::BeadRec> rec(n * N);
-  std::vector<int32_t> er34(n * 2 * N);
-  std::vector<double> oldr(n * 3 * N);
-  std::vector<dmd::CalEnt> cal(n * cs);
-  std::vector<dmd::RepScalars> scal(n);
-  std::string err;
-  auto work = [&](size_t k0, size_t k1) {
-    try {
-      dmd::HostReplicaInit init;
-      for (size_t k = k0; k < k1; k++) {
-        const int r = r0 + (int)k;
-        const bool same = sv_stride == 0 && k > k0;
-        if (!same)
-          dmd::build_replica_init(h->model, sv + k * sv_stride, bptnr ? bptnr + k * bp_stride : nullptr, h->tstar[r],
-                                  h->model.params.seed + (uint64_t)r, h->d.cal_stride, init);
-        if (same) {  // identical configuration: only the temperature-dependent scalars and the seed differ
-          dmd::HostReplicaInit tmp;
-          tmp.scal = init.scal;
-          dmd::init_scalars(tmp.scal, h->tstar[r], h->model.params.seed + (uint64_t)r);
-          init.scal = tmp.scal;
-          dmd::init_calendar(s, init.scal, h->d.cal_stride, init.cal);
-        }
-        std::copy(init.rec.begin(), init.rec.end(), rec.begin() + k * N);
-        std::copy(init.er34.begin(), init.er34.end(), er34.begin() + k * 2 * N);
-        std::copy(init.oldr.begin(), init.oldr.end(), oldr.begin() + k * 3 * N);
-        std::copy(init.cal.begin(), init.cal.end(), cal.begin() + k * cs);
-        scal[k] = init.scal;
-      }
-    } catch (const std::exception& e) {
-      err = e.what();
-    }
-  };
-  unsigned nt = std::thread::hardware_concurrency();
-  if (nt < 1) nt = 1;
-  if (nt > 32) nt = 32;
-  if (n < 2 * (size_t)nt) nt = 1;
-  if (nt == 1) {
-    work(0, n);
-  } else {
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < nt; t++) th.emplace_back(work, n * t / nt, n * (t + 1) / nt);
-    for (auto& x : th) x.join();
+  const size_t N = (size_t)s.N, n = (size_t)(r1 - r0), R = (size_t)h->d.n_replicas;
+  if (!h->stage_sv) {
+    h->stage_sv = dalloc<double>(h, R * N * 6);
+    h->stage_bp = dalloc<int32_t>(h, R * N);
   }
-  if (!err.empty()) throw std::runtime_error(err);
-  dmd::DevArrays& d = h->d;
-  const size_t rr = (size_t)r0;
-  be::h2d(d.rec + rr * N, rec.data(), n * N * sizeof(dmd::BeadRec));
-  be::h2d(d.er34 + rr * 2 * N, er34.data(), n * 2 * N * 4);
-  be::h2d(d.oldr + rr * 3 * N, oldr.data(), n * 3 * N * 8);
-  be::h2d(d.cal + rr * cs, cal.data(), n * cs * sizeof(dmd::CalEnt));
-  be::h2d(d.scal + rr, scal.data(), n * sizeof(dmd::RepScalars));
+  const size_t n_cfg = sv_stride ? n : 1;
+  be::h2d(h->stage_sv, sv, n_cfg * N * 6 * sizeof(double));
+  if (bptnr) be::h2d(h->stage_bp, bptnr, (bp_stride ? n : 1) * N * sizeof(int32_t));
+  be::h2d(h->temp_buf, h->tstar.data(), R * sizeof(double));
+  be::run_init(h->d, r0, (int)n, h->stage_sv, sv_stride, bptnr ? h->stage_bp : nullptr, bp_stride, h->temp_buf,
+               h->model.params.seed);
   for (int r = r0; r < r1; r++) h->loaded[r] = 1;
 }
 
@@ -313,8 +292,13 @@ int dmdb_run(dmdb_handle* h, int64_t n_events, dmdb_stats* stats) {
   int rc = all_loaded(h);
   if (rc) return rc;
   if (n_events < 0) return fail(h, DMDB_ERR_ARG, "n_events must be >= 0");
-  DMDB_TRY(h, be::run_op(h->d, dmd::OP_RUN, 0, h->d.n_replicas, n_events, nullptr, nullptr, &h->last_ms,
-                         &h->last_launches);)
+  // engine choice: one warp per replica fills the GPU from ~1000 replicas on; below that the CTA-per-replica
+  // engine (batched conservative commit, state in shared memory) is an order of magnitude faster per trajectory
+  int engine = h->model.params.engine;
+  if (engine == 0) engine = h->d.n_replicas >= 1184 ? 1 : 2;
+  if (engine == 2 && !be::block_engine_fits(h->model.sys)) engine = 1;
+  DMDB_TRY(h, be::run_op(h->d, engine == 2 ? dmd::OP_RUN_BLOCK : dmd::OP_RUN, 0, h->d.n_replicas, n_events, nullptr,
+                         nullptr, &h->last_ms, &h->last_launches);)
   rc = check_device_errors(h);
   if (rc) return rc;
   if (stats) return dmdb_get_replica_stats(h, -1, stats);
@@ -424,16 +408,13 @@ int dmdb_get_state_all(dmdb_handle* h, double* sv_all, int32_t* bptnr_all) {
   if (rc) return rc;
   const size_t N = (size_t)h->model.sys.N, R = (size_t)h->d.n_replicas;
   DMDB_TRY(h, {
-    std::vector<dmd::BeadRec> rec(R * N);
-    be::d2h(rec.data(), h->d.rec, R * N * sizeof(dmd::BeadRec));
-    for (size_t k = 0; k < R * N; k++) {
-      const dmd::BeadRec& b = rec[k];
-      if (sv_all) {
-        double* o = sv_all + 6 * k;
-        o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.vx; o[4] = b.vy; o[5] = b.vz;
-      }
-      if (bptnr_all) bptnr_all[k] = b.bptnr + 1;
+    if (!h->stage_sv) {
+      h->stage_sv = dalloc<double>(h, R * N * 6);
+      h->stage_bp = dalloc<int32_t>(h, R * N);
     }
+    be::run_pack(h->d, h->stage_sv, h->stage_bp);  // records -> sv(6,N) + bptnr on the device
+    if (sv_all) be::d2h(sv_all, h->stage_sv, R * N * 6 * sizeof(double));
+    if (bptnr_all) be::d2h(bptnr_all, h->stage_bp, R * N * sizeof(int32_t));
   })
   return DMDB_OK;
 }
@@ -523,6 +504,23 @@ int dmdb_get_event_log(dmdb_handle* h, int replica, int64_t first, int64_t n, dm
       be::d2h(out, h->d.log + (size_t)replica * std::max(h->model.sys.log_cap, 1) + first, (size_t)m * sizeof(dmdb_event));
     }
     if (n_out) *n_out = m;
+  })
+  return DMDB_OK;
+}
+
+int dmdb_get_batch_stats(dmdb_handle* h, int replica, int64_t out[16]) {
+  if (!h || !out) return DMDB_ERR_ARG;
+  if (replica >= 0) {
+    int rc = check_replica(h, replica, false);
+    if (rc) return rc;
+  }
+  DMDB_TRY(h, {
+    const int R = h->d.n_replicas;
+    std::vector<long long> st((size_t)R * 16);
+    be::d2h(st.data(), h->d.blkstat, st.size() * sizeof(long long));
+    for (int k = 0; k < 16; k++) out[k] = 0;
+    for (int r = (replica < 0 ? 0 : replica); r < (replica < 0 ? R : replica + 1); r++)
+      for (int k = 0; k < 16; k++) out[k] += st[(size_t)r * 16 + k];
   })
   return DMDB_OK;
 }

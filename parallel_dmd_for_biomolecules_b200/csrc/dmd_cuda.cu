@@ -1,7 +1,9 @@
 // dmd_cuda.cu -- libdmdb200.so: CUDA backend (sm_100a) of the C ABI in include/dmdb200.h.
 //
-// Kernels (one warp per replica; 4 replicas per CTA; the 28x28 pair tables are staged in shared memory):
-//   dmd_event_loop_kernel    the persistent event loop, main.F90:484-1258 (dmdb_run)
+// Kernels (one warp per replica; 16 replicas per CTA; the 28x28 pair tables and hot constants are staged in shared memory):
+//   dmd_event_loop_kernel    the persistent event loop, main.F90:484-1258 (dmdb_run, engine 1: warp per replica)
+//   dmd_block_loop_kernel    the same loop with one CTA per replica, state in shared memory, batched
+//                            conservative commit of independent events (dmdb_run, engine 2; dmd_block.h)
 //   dmd_start_kernel         run start: first ghost time (main.F90:408-416) + nbor() + events()
 //   dmd_nbor_kernel          cell_add.f + nbor.f  (dmdb_nbor)
 //   dmd_predict_all_kernel   events.f             (dmdb_predict_all)
@@ -15,6 +17,7 @@
 #include <stdexcept>
 #include <string>
 
+#include "dmd_block.h"
 #include "dmd_engine.h"
 #include "dmd_types.h"
 
@@ -26,17 +29,36 @@
 
 namespace dmd {
 
-constexpr int WARPS_PER_CTA = 4;
+#ifndef DMD_WPC
+#define DMD_WPC 16  // one 16-warp CTA per SM shares ONE shared-memory copy of the tables; the rest stays L1
+#endif
+constexpr int WARPS_PER_CTA = DMD_WPC;
 #ifndef DMD_MIN_CTAS
-#define DMD_MIN_CTAS 4  // 4 CTAs x 4 warps per SM at <= 128 registers per thread
+#define DMD_MIN_CTAS 1  // 16 warps per SM at <= 128 registers per thread
 #endif
 
-__device__ __forceinline__ const PairTables* stage_tables(const DevArrays& d, PairTables* smem) {
+// read-only constants of the hot loop, copied into shared memory once per CTA
+struct SmemConsts {
+  PairTables tab;
+  HotConst hot;
+  double bl[6 * HOT_MAX_RES];
+};
+__device__ __forceinline__ Staged stage_consts(const DevArrays& d, SmemConsts* smem) {
   const double* src = reinterpret_cast<const double*>(d.tables);
-  double* dst = reinterpret_cast<double*>(smem);
+  double* dst = reinterpret_cast<double*>(&smem->tab);
   for (int k = threadIdx.x; k < (int)(sizeof(PairTables) / 8); k += blockDim.x) dst[k] = src[k];
+  src = reinterpret_cast<const double*>(d.hot);
+  dst = reinterpret_cast<double*>(&smem->hot);
+  for (int k = threadIdx.x; k < (int)(sizeof(HotConst) / 8); k += blockDim.x) dst[k] = src[k];
+  const bool bl_fits = d.nres <= HOT_MAX_RES;
+  if (bl_fits)
+    for (int k = threadIdx.x; k < 6 * d.nres; k += blockDim.x) smem->bl[k] = d.bl[k];
   __syncthreads();
-  return smem;
+  Staged st;
+  st.tab = &smem->tab;
+  st.hot = &smem->hot;
+  st.bl = bl_fits ? smem->bl : d.bl;
+  return st;
 }
 
 __device__ __forceinline__ int32_t* warp_queue() {
@@ -50,8 +72,8 @@ __device__ __forceinline__ int replica_of_warp(int r0, int nrep) {
 }
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, DMD_MIN_CTAS) dmd_event_loop_kernel(DevArrays d, int r0, int nrep, long long n_events) {
-  __shared__ PairTables stab;
-  const PairTables* tab = stage_tables(d, &stab);
+  __shared__ SmemConsts sconst;
+  const Staged tab = stage_consts(d, &sconst);
   int rid = replica_of_warp(r0, nrep);
   if (rid < 0) return;
   Rep r;
@@ -60,9 +82,145 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, DMD_MIN_CTAS) dmd_event_lo
   rep_save(r);
 }
 
+// ---- CTA-per-replica engine -----------------------------------------------------------------------------------
+// dynamic shared memory: BlkShared | PairTables | cascade queues | claim[N+3] | (rec[N] | cal[stride] | er34[2N])
+struct BlkLayout {
+  size_t tab, cq, claim, meta, nup, ndn, rec, cal, er34, total;
+  bool state;  // bead records / calendar / er34 resident in shared memory
+};
+__host__ __device__ inline size_t blk_align(size_t x) { return (x + 127) & ~(size_t)127; }
+__host__ __device__ inline BlkLayout blk_layout(int N, int cal_stride, size_t limit) {
+  BlkLayout L;
+  size_t off = blk_align(sizeof(BlkShared));
+  L.tab = off; off += blk_align(sizeof(SmemConsts));
+  L.cq = off; off += blk_align((size_t)BK_MAXW * CQ_CAP * 4);
+  L.claim = off; off += blk_align(((size_t)N + 3) * 4);
+  L.meta = off; off += blk_align((size_t)N * 4);
+  L.nup = off; off += blk_align((size_t)N * 2);
+  L.ndn = off; off += blk_align((size_t)N * 2);
+  L.rec = off;
+  size_t st = off + blk_align((size_t)N * sizeof(BeadRec));
+  L.cal = st; st += blk_align((size_t)cal_stride * sizeof(CalEnt));
+  L.er34 = st; st += blk_align((size_t)N * 8);
+  L.state = st <= limit;
+  L.total = L.state ? st : off;
+  return L;
+}
+
+__global__ void __launch_bounds__(BK_MAXW * 32, 1) dmd_block_loop_kernel(DevArrays d, int r0, int nrep, long long n_events,
+                                                                         unsigned smem_limit) {
+  extern __shared__ __align__(128) unsigned char blk_smem[];
+  const int N = d.sys->N;
+  const BlkLayout L = blk_layout(N, d.cal_stride, smem_limit);
+  BlkShared& S = *reinterpret_cast<BlkShared*>(blk_smem);
+  SmemConsts* sconst = reinterpret_cast<SmemConsts*>(blk_smem + L.tab);
+  int32_t* cq = reinterpret_cast<int32_t*>(blk_smem + L.cq);
+  uint32_t* claim = reinterpret_cast<uint32_t*>(blk_smem + L.claim);
+  const Staged tab = stage_consts(d, sconst);
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5, tid = threadIdx.x, nt = blockDim.x;
+  for (int rr = blockIdx.x; rr < nrep; rr += gridDim.x) {
+    const int rid = r0 + rr;
+    Rep r;
+    rep_bind(r, d, tab, cq + w * CQ_CAP, rid);
+    BeadRec* const grec = r.rec;
+    CalEnt* const gcal = r.cal;
+    int32_t* const ger34 = r.er34;
+    uint16_t* const gnup = r.nup;
+    uint16_t* const gndn = r.ndn;
+    {  // topology words and list lengths are always resident
+      uint32_t* smeta = reinterpret_cast<uint32_t*>(blk_smem + L.meta);
+      uint16_t* snup = reinterpret_cast<uint16_t*>(blk_smem + L.nup);
+      uint16_t* sndn = reinterpret_cast<uint16_t*>(blk_smem + L.ndn);
+      for (int k = tid; k < N; k += nt) {
+        smeta[k] = d.meta[k];
+        snup[k] = gnup[k];
+        sndn[k] = gndn[k];
+      }
+      r.c.meta = smeta;
+      r.nup = snup;
+      r.ndn = sndn;
+    }
+    if (L.state) {  // stage the replica into shared memory (16-byte vector copies)
+      uint4* srec = reinterpret_cast<uint4*>(blk_smem + L.rec);
+      uint4* scal = reinterpret_cast<uint4*>(blk_smem + L.cal);
+      int2* ser = reinterpret_cast<int2*>(blk_smem + L.er34);
+      const uint4* g4 = reinterpret_cast<const uint4*>(grec);
+      for (int k = tid; k < N * 4; k += nt) srec[k] = g4[k];
+      const uint4* c4 = reinterpret_cast<const uint4*>(gcal);
+      for (int k = tid; k < d.cal_stride; k += nt) scal[k] = c4[k];
+      const int2* e2 = reinterpret_cast<const int2*>(ger34);
+      for (int k = tid; k < N; k += nt) ser[k] = e2[k];
+      r.rec = reinterpret_cast<BeadRec*>(srec);
+      r.cal = reinterpret_cast<CalEnt*>(scal);
+      r.er34 = reinterpret_cast<int32_t*>(ser);
+    }
+    for (int k = tid; k < N + 3; k += nt) claim[k] = CLAIM_FREE;
+    if (w != 0) r.n_pair_pred = r.n_nbr_visits = 0;
+    if (tid == 0) {
+      S.coll = r.coll;
+      S.target = r.coll + n_events;
+      S.window = r.interval * 0.02;
+      S.error = r.error;
+      S.error_info = r.error_info;
+      S.st_rounds = S.st_exec = S.st_rollback = S.st_conflict = S.st_cold = 0;
+      S.n_pair_pred = S.n_nbr_visits = 0;
+      S.n_cand = 0;
+      S.tlast = -1.0;
+      for (int q = 0; q < 8; q++) S.cyc[q] = 0;
+      for (int q = 0; q < 32; q++) S.nevents[q] = 0;
+    }
+    __syncthreads();
+    blk_run(S, r, claim, w, nw);
+    if (w != 0 && Warp::lane() == 0) {
+      blk_atomic_add64(&S.n_pair_pred, r.n_pair_pred);
+      blk_atomic_add64(&S.n_nbr_visits, r.n_nbr_visits);
+    }
+    __syncthreads();
+    for (int k = tid; k < N; k += nt) {  // list lengths may have changed (rebuilds)
+      gnup[k] = r.nup[k];
+      gndn[k] = r.ndn[k];
+    }
+    r.nup = gnup;
+    r.ndn = gndn;
+    r.c.meta = d.meta;
+    if (L.state) {
+      uint4* g4 = reinterpret_cast<uint4*>(grec);
+      const uint4* srec = reinterpret_cast<const uint4*>(blk_smem + L.rec);
+      for (int k = tid; k < N * 4; k += nt) g4[k] = srec[k];
+      uint4* c4 = reinterpret_cast<uint4*>(gcal);
+      const uint4* scal = reinterpret_cast<const uint4*>(blk_smem + L.cal);
+      for (int k = tid; k < d.cal_stride; k += nt) c4[k] = scal[k];
+      int2* e2 = reinterpret_cast<int2*>(ger34);
+      const int2* ser = reinterpret_cast<const int2*>(blk_smem + L.er34);
+      for (int k = tid; k < N; k += nt) e2[k] = ser[k];
+      r.rec = grec;
+      r.cal = gcal;
+      r.er34 = ger34;
+    }
+    __syncthreads();
+    if (w == 0) {
+      r.n_pair_pred += S.n_pair_pred;
+      r.n_nbr_visits += S.n_nbr_visits;
+      if (S.error && !r.error) {
+        r.error = S.error;
+        r.error_info = S.error_info;
+      }
+      rep_save(r);
+      rebuild_all_groups(r);  // the warp engine's group minima, so that both engines can alternate on one handle
+      if (Warp::lane() == 0) {
+        for (int q = 0; q < 32; q++) r.sc->nevents[q] += S.nevents[q];
+        long long* st = d.blkstat + (size_t)rid * 16;
+        st[0] += S.st_rounds; st[1] += S.st_exec; st[2] += S.st_rollback; st[3] += S.st_conflict; st[4] += S.st_cold;
+        for (int q = 0; q < 7; q++) st[8 + q] += S.cyc[q];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_start_kernel(DevArrays d, int r0, int nrep) {
-  __shared__ PairTables stab;
-  const PairTables* tab = stage_tables(d, &stab);
+  __shared__ SmemConsts sconst;
+  const Staged tab = stage_consts(d, &sconst);
   int rid = replica_of_warp(r0, nrep);
   if (rid < 0) return;
   Rep r;
@@ -78,8 +236,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_start_kernel(DevArrays
 }
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_nbor_kernel(DevArrays d, int r0, int nrep) {
-  __shared__ PairTables stab;
-  const PairTables* tab = stage_tables(d, &stab);
+  __shared__ SmemConsts sconst;
+  const Staged tab = stage_consts(d, &sconst);
   int rid = replica_of_warp(r0, nrep);
   if (rid < 0) return;
   Rep r;
@@ -89,8 +247,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_nbor_kernel(DevArrays 
 }
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_predict_all_kernel(DevArrays d, int r0, int nrep) {
-  __shared__ PairTables stab;
-  const PairTables* tab = stage_tables(d, &stab);
+  __shared__ SmemConsts sconst;
+  const Staged tab = stage_consts(d, &sconst);
   int rid = replica_of_warp(r0, nrep);
   if (rid < 0) return;
   Rep r;
@@ -103,13 +261,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_sync_positions_kernel(
   int rid = replica_of_warp(r0, nrep);
   if (rid < 0) return;
   Rep r;
-  rep_bind(r, d, d.tables, warp_queue(), rid);
+  rep_bind(r, d, staged_global(d), warp_queue(), rid);
   sync_positions(r);
 }
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_energy_kernel(DevArrays d, int r0, int nrep, OutRec* eout) {
-  __shared__ PairTables stab;
-  const PairTables* tab = stage_tables(d, &stab);
+  __shared__ SmemConsts sconst;
+  const Staged tab = stage_consts(d, &sconst);
   int rid = replica_of_warp(r0, nrep);
   if (rid < 0) return;
   Rep r;
@@ -120,8 +278,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_energy_kernel(DevArray
 }
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_retemp_kernel(DevArrays d, int r0, int nrep, const double* tstar_new) {
-  __shared__ PairTables stab;
-  const PairTables* tab = stage_tables(d, &stab);
+  __shared__ SmemConsts sconst;
+  const Staged tab = stage_consts(d, &sconst);
   int rid = replica_of_warp(r0, nrep);
   if (rid < 0) return;
   const double tn = tstar_new[rid];
@@ -130,6 +288,33 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_retemp_kernel(DevArray
   rep_bind(r, d, tab, warp_queue(), rid);
   retemp(r, tn);
   rep_save(r);
+}
+
+// run start on the device: raw sv / bptnr (staged by dmdb_set_state*) -> every per-replica array
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_init_kernel(DevArrays d, int r0, int nrep, const double* sv,
+                                                                      size_t sv_stride, const int32_t* bp, size_t bp_stride,
+                                                                      const double* tstar, unsigned long long seed0) {
+  __shared__ SmemConsts sconst;
+  const Staged tab = stage_consts(d, &sconst);
+  int rid = replica_of_warp(r0, nrep);
+  if (rid < 0) return;
+  Rep r;
+  rep_bind(r, d, tab, warp_queue(), rid);
+  const size_t k = (size_t)(rid - r0);
+  init_replica(r, sv + k * sv_stride, bp ? bp + k * bp_stride : nullptr, tstar[rid], seed0 + (unsigned long long)rid,
+               d.nc_beads, d.n_nc, d.cal_stride);
+  rep_save(r);
+}
+
+// device state -> the reference's sv(6,N) and bptnr(N) (1-based), for dmdb_get_state_all
+__global__ void dmd_pack_kernel(DevArrays d, double* sv, int32_t* bp) {
+  const size_t n = (size_t)d.n_replicas * d.n_beads;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    const BeadRec b = d.rec[k];
+    double* o = sv + 6 * k;
+    o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.vx; o[4] = b.vy; o[5] = b.vz;
+    bp[k] = b.bptnr + 1;
+  }
 }
 
 __global__ void dmd_evcode_kernel(DevArrays d, int rid, int n_pairs, int32_t* buf) {
@@ -192,6 +377,34 @@ inline void fill_i32(int32_t* d, int v, size_t n) {
   else throw std::runtime_error("fill_i32: unsupported value");
 }
 
+static size_t g_smem_optin = 0;
+inline size_t smem_optin() {
+  if (!g_smem_optin) {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    g_smem_optin = (size_t)v;
+  }
+  return g_smem_optin;
+}
+// the CTA-per-replica engine needs at least its fixed part (tables, claims, undo logs) in shared memory
+inline bool block_engine_fits(const dmd::SysConst& s) {
+  return dmd::blk_layout(s.N, s.ngroups * 32, smem_optin()).total <= smem_optin();
+}
+
+inline void run_init(const dmd::DevArrays& d, int r0, int nrep, const double* sv, size_t sv_stride, const int32_t* bp,
+                     size_t bp_stride, const double* tstar, unsigned long long seed0) {
+  using namespace dmd;
+  const int grid = (nrep + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  dmd_init_kernel<<<grid, WARPS_PER_CTA * 32, 0, g_stream>>>(d, r0, nrep, sv, sv_stride, bp, bp_stride, tstar, seed0);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(g_stream));
+}
+inline void run_pack(const dmd::DevArrays& d, double* sv, int32_t* bp) {
+  dmd::dmd_pack_kernel<<<148 * 8, 256, 0, g_stream>>>(d, sv, bp);
+  CUDA_OK(cudaGetLastError());
+}
+
 // one launcher per device operation; times the kernel with CUDA events on the launching stream
 inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long arg, int32_t* ibuf, dmd::OutRec* eout,
                    double* ms, int* launches) {
@@ -208,6 +421,17 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
     case 5: dmd_energy_kernel<<<grid, block, 0, g_stream>>>(d, r0, nrep, eout); break;
     case 6: dmd_evcode_kernel<<<((int)arg + 127) / 128, 128, 0, g_stream>>>(d, r0, (int)arg, ibuf); break;
     case 7: dmd_retemp_kernel<<<grid, block, 0, g_stream>>>(d, r0, nrep, (const double*)ibuf); break;
+    case 8: {
+      int dev = 0, sms = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const BlkLayout L = blk_layout(d.n_beads, d.cal_stride, smem_optin());  // host-side copies: d.sys is a device pointer
+      if (L.total > smem_optin()) throw std::runtime_error("system too large for the CTA-per-replica engine");
+      CUDA_OK(cudaFuncSetAttribute(dmd_block_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+      const int g = nrep < sms ? nrep : sms;
+      dmd_block_loop_kernel<<<g, BK_MAXW * 32, L.total, g_stream>>>(d, r0, nrep, arg, (unsigned)smem_optin());
+      break;
+    }
     default: throw std::runtime_error("unknown device op");
   }
   CUDA_OK(cudaGetLastError());

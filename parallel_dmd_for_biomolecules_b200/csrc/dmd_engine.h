@@ -60,10 +60,25 @@ DMD_DEV void rep_load_scalars(Rep& r) {
   r.n_log = q.n_log; r.n_out = q.n_out; r.error = q.error; r.error_info = q.error_info;
 }
 
-DMD_DEV void rep_bind(Rep& r, const DevArrays& d, const PairTables* tab, int32_t* cq, int rid) {
+struct Staged {  // the shared-memory copies of the read-only tables (global pointers in the host trace build)
+  const PairTables* tab;
+  const HotConst* hot;
+  const double* bl;
+};
+DMD_DEV Staged staged_global(const DevArrays& d) {
+  Staged st;
+  st.tab = d.tables;
+  st.hot = d.hot;
+  st.bl = d.bl;
+  return st;
+}
+
+DMD_DEV void rep_bind(Rep& r, const DevArrays& d, const Staged& st, int32_t* cq, int rid) {
   const SysConst* s = d.sys;
   r.c.sys = s;
-  r.c.tab = tab;
+  r.c.tab = st.tab;
+  r.c.hot = st.hot;
+  r.c.bl = st.bl;
   r.c.meta = d.meta;
   r.c.chain = d.chain;
   const int N = s->N;
@@ -239,76 +254,142 @@ DMD_DEV int type_of(int packed) { return (int)(int8_t)(packed & 0xff); }
 DMD_DEV int sc_of(int packed) { return (packed >> 8) & 0xff; }
 
 // ---------------------------------------------------------------------------------------------------------
-// prediction pass for bead a (hot): lanes cover, in this order,
-//   [0, nu)            up-list partners j > a          } events.f:26-57 / eventredo_up.f : owner a
-//   [nu, nu+3)         aux slots extra_repuls(a,1:3)>a }
-//   [nF, nF+nd)        down-list beads l < a           } eventredo_down.f : owner l, or cascade when
-//   [nF+nd, nF+nd+3)   aux slots extra_repuls(a,1:3)<a }   nptnr(l) == a (partial_events.f:73-96)
-// with_down = false restricts the pass to the first two ranges (a cascaded full re-prediction).
-// Lanes of the last two ranges that need a cascade push their bead on the queue r.cq.
+// partial_events.f:16-201 -- re-prediction after an event on (i, j).
+//
+// The Fortran does full(i), full(j), down(i), down(j), with a full re-prediction of a down-neighbour l whenever
+// nptnr(l) was i or j (a "cascade").  Here each colliding bead gets ONE pass whose lanes cover all its items, and
+// the cascades of both beads are collected and done at the end, several beads per pass.  The items of a bead a,
+// in the Fortran's evaluation order:
+//   [0, nu)            up-list partners b > a           } events.f:26-57 / eventredo_up.f : owner a ("full")
+//   [nu, nu+3)         aux slots extra_repuls(a,1:3) > a }
+//   [nF, nF+nd)        down-list beads l < a            } eventredo_down.f : owner l, or cascade when
+//   [nF+nd, nF+nd+3)   aux slots extra_repuls(a,1:3) < a }   nptnr(l) == a (partial_events.f:73-96)
+// Pair times depend on bead records only, never on the calendar.  The calendar updates are applied for i, then
+// (after a warp sync, re-reading the entries) for j; cascades run last with the lanes split into segments.
+//
+// Equivalence with the Fortran order (exact ties in time between different pairs excepted): a cascade rewrites
+// cal[l] with a pure function of the records, so it gives the same entry whenever it runs, and any earlier
+// lowering of that entry is overwritten; compare-and-lower operations on an entry whose partner is neither i nor
+// j commute; an entry whose partner was i (j) is either queued by i's (j's) operation, or -- if j's (i's)
+// operation came first and replaced it -- was beaten by a pair time that is then also the full minimum.
 // ---------------------------------------------------------------------------------------------------------
-DMD_DEV void predict_pass(Rep& r, int a, bool with_down, int skip, int& cqn) {
-  // level-1 loads, all independent: the record of a, its list lengths, and (speculatively, before the lengths
-  // are known) the first 32 entries of both lists -- one entry per lane
+// Block engine (dmd_block.h) only: an event executed speculatively records every calendar entry it overwrites
+// (index + old entry) so that it can be rolled back, and the earliest event time it creates.
+struct Undo {
+  int32_t* idx;
+  CalEnt* old;
+  int n, cap;
+  double newmin;
+};
+
+// where a pass finds the two lists of its bead: the replica's own arrays, or (block engine) the copy staged in
+// shared memory when the event's footprint was claimed
+struct ListRef {
+  const uint32_t* up;
+  const uint32_t* dn;
+  int nu, nd;
+};
+
+// (value, key) arg-min over the lanes of `mask` (a segment of the warp); all lanes of the segment get the result
+DMD_DEV void seg_argmin(double& v, int& key, unsigned mask) {
+#if DMD_W > 1
+  unsigned hi, lo;
+  ord_split(v, hi, lo);
+  const unsigned mhi = __reduce_min_sync(mask, hi);
+  const bool c1 = hi == mhi;
+  const unsigned mlo = __reduce_min_sync(mask, c1 ? lo : 0xffffffffu);
+  const bool c2 = c1 && lo == mlo;
+  const unsigned mkey = __reduce_min_sync(mask, c2 ? (unsigned)key : 0xffffffffu);
+  v = ord_join(mhi, mlo);
+  key = (int)mkey;
+#endif
+}
+
+// ONE pass = ONE copy of the prediction code in the hot loop (the loop must stay resident in the instruction
+// cache while every warp of the SM sits at a different program counter).  The warp is split into G = 1, 2 or 4
+// segments of SEG lanes; segment g handles bead beads[g]:
+//   main pass      G = 1, with_down: all items of a colliding bead (full items feed the running minimum of the
+//                  bead, down items lower cal[b] -- eventredo_down.f:70-77 -- or queue b for a cascade)
+//   cascade pass   G beads at once, full items only (events.f:26-57 for one bead each)
+template <bool BLK>
+DMD_DEV void segmented_pass(Rep& r, int a, bool act, int sh, bool with_down, int skip, const ListRef* lr, int& cqn,
+                            Undo* u) {
+#if DMD_W > 1
+  const int SEG = DMD_W >> sh;
+  const int g = Warp::lane() >> (5 - sh), pl = Warp::lane() & (SEG - 1);
+  const unsigned segmask = (sh == 0 ? 0xffffffffu : ((1u << SEG) - 1u)) << (g * SEG);
+#else
+  const int SEG = 1, pl = 0;
+  const unsigned segmask = 1u;
+#endif
+  // ---- level-1 loads, all independent: record, list lengths and (before the lengths are known) the first SEG
+  // entries of the lists, one per lane
   const size_t lbase = (size_t)a * r.cap;
+  const uint32_t* const upl = lr ? lr->up : r.up + lbase;
+  const uint32_t* const dnl = lr ? lr->dn : r.dn + lbase;
 #if DMD_W > 1
   uint32_t eu0 = 0, ed0 = 0;
-  if (Warp::lane() < r.cap) {
-    eu0 = r.up[lbase + Warp::lane()];
-    if (with_down) ed0 = r.dn[lbase + Warp::lane()];
+  if (pl < r.cap) {
+    eu0 = upl[pl];
+    if (with_down) ed0 = dnl[pl];
   }
 #endif
   const BeadRec ra = r.rec[a];
   const uint32_t ma = r.c.meta[a];
-  const int nu = r.nup[a];
-  const int nd = with_down ? (int)r.ndn[a] : 0;
+  const int nu = act ? (lr ? lr->nu : (int)r.nup[a]) : -3;
+  const int nd = with_down ? (lr ? lr->nd : (int)r.ndn[a]) : 0;
   const int er3 = r.er34[2 * a];
   const int nF = nu + 3, total = with_down ? nF + nd + 3 : nF;
+  int tmax = total;
+#if DMD_W > 1
+  if (sh) tmax = (int)__reduce_max_sync(0xffffffffu, (unsigned)(total > 0 ? total : 0));
+#endif
+  r.n_pair_pred += sh ? warp_sum(pl == 0 && act ? total : 0) : total;
+  r.n_nbr_visits += sh ? warp_sum(pl == 0 && act ? nu : 0) : nu + nd;
   double best = r.interval_max + LTSTEP - r.tfalse;
   int bpos = 0x7fffffff, bj = -1, btype = -1;
-  r.n_pair_pred += total;
-  r.n_nbr_visits += nu + nd;
-  for (int base = 0; base < total; base += DMD_W) {
-    const int p = base + Warp::lane();
+#pragma unroll 1
+  for (int base = 0; base < tmax; base += SEG) {
+    const int p = base + pl;
     int b = -1, sc = 1;  // the other bead of the pair and the pair's static class
     const bool full = p < nF;
     const int q = p - nF;  // index into the down list
 #if DMD_W > 1
-    const uint32_t edq = Warp::shfl((int)ed0, q & 31);
+    const uint32_t edq = (uint32_t)Warp::shfl((int)ed0, q & 31);  // main pass only (G = 1)
 #endif
     if (p < nu) {
 #if DMD_W > 1
-      uint32_t e = base == 0 ? eu0 : r.up[lbase + p];
+      const uint32_t e = base == 0 ? eu0 : upl[p];
 #else
-      uint32_t e = r.up[lbase + p];
+      const uint32_t e = upl[p];
 #endif
       b = (int)(e & NB_MASK);
       sc = (int)(e >> NB_SHIFT);
     } else if (p < nF) {
-      int k = p - nu;
+      const int k = p - nu;
       b = k == 0 ? ra.er1 : (k == 1 ? ra.er2 : er3);
       if (b <= a) b = -1;  // events.f:77
     } else if (q < nd) {
 #if DMD_W > 1
-      uint32_t e = q < 32 ? edq : r.dn[lbase + q];
+      const uint32_t e = q < 32 ? edq : dnl[q];
 #else
-      uint32_t e = r.dn[lbase + q];
+      const uint32_t e = dnl[q];
 #endif
       b = (int)(e & NB_MASK);
       sc = (int)(e >> NB_SHIFT);
       if (b == skip) b = -1;  // partial_events.f:136
     } else if (p < total) {
-      int k = q - nd;
+      const int k = q - nd;
       b = k == 0 ? ra.er1 : (k == 1 ? ra.er2 : er3);
       if (!(b >= 0 && b < a)) b = -1;  // partial_events.f:100,166
     }
     bool need_full = false;
     int changed = -1;
+    CalEnt eb;
+    eb.t = 0.0; eb.ptnr = -1; eb.type = -1;
     if (b >= 0) {
       // level-2 loads, all depending on b only
       const BeadRec rb = r.rec[b];
-      CalEnt eb;
-      eb.t = 0.0; eb.ptnr = -1; eb.type = -1;
       uint32_t mlo = ma;
       if (!full) {
         eb = r.cal[b];
@@ -321,12 +402,12 @@ DMD_DEV void predict_pass(Rep& r, int a, bool with_down, int skip, int& cqn) {
         double tij = T_NONE;
         int type = -1;
         {  // one prediction site for both orientations (owner = lower index: a when full, b otherwise)
-          const Geom g = pair_geom(ra, rb, r.tfalse);
-          const double rijsq = g.rx * g.rx + g.ry * g.ry + g.rz * g.rz;
-          const double vijsq = g.vx * g.vx + g.vy * g.vy + g.vz * g.vz;
+          const Geom gm = pair_geom(ra, rb, r.tfalse);
+          const double rijsq = gm.rx * gm.rx + gm.ry * gm.ry + gm.rz * gm.rz;
+          const double vijsq = gm.vx * gm.vx + gm.vy * gm.vy + gm.vz * gm.vz;
           const int idlo = full ? ra.ident : rb.ident, idhi = full ? rb.ident : ra.ident;
           const bool bonded = full ? ra.bptnr == b : rb.bptnr == a;
-          pair_time_core(r.c, code, g.bij, rijsq, vijsq, idlo, idhi, mlo, bonded, tij, type);
+          pair_time_core(r.c, code, gm.bij, rijsq, vijsq, idlo, idhi, mlo, bonded, tij, type);
         }
         if (full) {
           if (tij < best) {  // strict: first in evaluation order wins (events.f:53)
@@ -344,72 +425,128 @@ DMD_DEV void predict_pass(Rep& r, int a, bool with_down, int skip, int& cqn) {
             ne.type = pack_type(type, sc);
             r.cal[b] = ne;
             changed = b;
+            if (BLK && tij < u->newmin) u->newmin = tij;
           }
         }
       }
     }
     if (with_down) {
-      mark_dirty_lanes(r, changed);
-      unsigned m = Warp::ballot(need_full);
+      if (BLK) {  // undo log of the lowered entries (eb = the old entry of this lane's bead)
+        const unsigned mc = Warp::ballot(changed >= 0);
+        if (mc) {
+          const int pos = u->n + dmd_popc(mc & ((1u << Warp::lane()) - 1u));
+          if (changed >= 0 && pos < u->cap) {
+            u->idx[pos] = changed;
+            u->old[pos] = eb;
+          }
+          u->n += dmd_popc(mc);
+        }
+      } else {
+        mark_dirty_lanes(r, changed);
+      }
+      const unsigned m = Warp::ballot(need_full);
       if (m) {
-        int pos = cqn + dmd_popc(m & ((1u << Warp::lane()) - 1u));
+        const int pos = cqn + dmd_popc(m & ((1u << Warp::lane()) - 1u));
         if (need_full && pos < CQ_CAP) r.cq[pos] = b;
         cqn += dmd_popc(m);
       }
     }
   }
+  // ---- the minimum of each segment's full items -> cal[a]; the lane that holds it writes the entry (a segment
+  // without any event: its first lane)
   double wbest = best;
   int wpos = bpos;
-  warp_argmin(wbest, wpos);
-  unsigned owner = Warp::ballot(bpos == wpos && bpos != 0x7fffffff);
-  if (owner) {
-    int src = dmd_ffs(owner) - 1;
-    bj = Warp::shfl(bj, src);
-    btype = Warp::shfl(btype, src);
-  } else {
-    bj = -1;
-    btype = -1;
-  }
-  if (Warp::lane() == 0) {
-    CalEnt ne;
-    ne.t = wbest + r.tfalse;
-    ne.ptnr = bj;
-    ne.type = btype;
+  seg_argmin(wbest, wpos, segmask);
+  const bool mine = act && bpos == wpos && bpos != 0x7fffffff;
+  const unsigned any_mine = Warp::ballot(mine) & segmask;
+  const bool writer = act && (any_mine ? mine : pl == 0);
+  CalEnt ne;
+  ne.t = wbest + r.tfalse;
+  ne.ptnr = any_mine ? bj : -1;
+  ne.type = any_mine ? btype : -1;
+  CalEnt old;
+  old.t = 0.0; old.ptnr = -1; old.type = -1;
+  if (writer) {
+    if (BLK) old = r.cal[a];
     r.cal[a] = ne;
   }
-  mark_dirty(r, a >> 5);
+  if (BLK) {
+    const unsigned mw = Warp::ballot(writer);
+    const int pos = u->n + dmd_popc(mw & ((1u << Warp::lane()) - 1u));
+    if (writer && pos < u->cap) {
+      u->idx[pos] = a;
+      u->old[pos] = old;
+    }
+    u->n += dmd_popc(mw);
+    if (writer && ne.t < u->newmin) u->newmin = ne.t;
+  } else {
+    mark_dirty_lanes(r, writer ? a : -1);
+  }
 }
 
-// partial_events.f:16-201.  Order used: full(i), down(i) [+cascades], full(j), down(j) [+cascades]; this is
-// equivalent to the Fortran's full(i), full(j), down(i), down(j) because full(j) only rewrites entry j, which
-// down(i) never reads (its beads are < i < j), see DESIGN.md "pass order".
 DMD_DEV void repuls_del_b(Rep& r, int n, int cb);
 
-DMD_DEV void partial_events(Rep& r, int i, int j, bool xpulse_del) {
+template <bool BLK>
+DMD_DEV void partial_events_t(Rep& r, int i, int j, bool xpulse_del, Undo* u, const ListRef* li, const ListRef* lj) {
   Warp::sync();
-  int cqn = 0, stage = 0;
+  int cqn = 0, stage = 0, idx = 0;
+#pragma unroll 1
   while (true) {
-    int a, skip = -1;
-    bool with_down;
-    if (cqn > 0) {
-      if (cqn > CQ_CAP) {
-        set_error(r, DMD_E_NBR_CAP, cqn);
-        break;
-      }
-      Warp::sync();
-      a = r.cq[--cqn];
-      with_down = false;
-    } else if (stage < 2) {
+    int a, skip = -1, sh = 0;
+    bool with_down, act = true;
+    const ListRef* lr = nullptr;
+    if (stage < 2) {  // the two colliding beads, one after the other
       a = stage == 0 ? i : j;
       skip = stage == 0 ? -1 : i;
+      lr = stage == 0 ? li : lj;
       stage++;
-      if (a < 0) continue;
+      if (a < 0) continue;  // ghost event: one bead only (main.F90:1049)
       with_down = true;
     } else {
-      break;
+      if (stage == 2) {  // all down items are done: prepare the cascade queue
+        stage = 3;
+        if (cqn > CQ_CAP) {
+          set_error(r, DMD_E_NBR_CAP, cqn);
+          cqn = 0;
+        }
+        if (cqn > 1) {  // a bead queued by both i and j is re-predicted once
+          int keep_n = 0;
+          for (int base = 0; base < cqn; base += DMD_W) {
+            const int k = base + Warp::lane();
+            bool keep = false;
+            int v = -1;
+            if (k < cqn) {
+              v = r.cq[k];
+              keep = true;
+              for (int m = 0; m < k; m++)
+                if (r.cq[m] == v) keep = false;
+            }
+            Warp::sync();
+            const unsigned mk = Warp::ballot(keep);
+            if (keep) r.cq[keep_n + dmd_popc(mk & ((1u << Warp::lane()) - 1u))] = v;
+            keep_n += dmd_popc(mk);
+            Warp::sync();
+          }
+          cqn = keep_n;
+        }
+      }
+      if (idx >= cqn) break;
+      // cascades, several beads per pass: segment count by the queue length only (no size look-up: that would
+      // put a dependent load in front of the pass); a list longer than its segment takes another trip
+      const int rem = cqn - idx;
+#if DMD_W > 1
+      sh = rem >= 3 ? 2 : (rem == 2 ? 1 : 0);
+      const int g = Warp::lane() >> (5 - sh);
+#else
+      const int g = 0;
+#endif
+      act = g < rem;
+      a = r.cq[idx + (act ? g : 0)];
+      idx += rem < (1 << sh) ? rem : (1 << sh);
+      with_down = false;
     }
-    predict_pass(r, a, with_down, skip, cqn);
-    Warp::sync();
+    segmented_pass<BLK>(r, a, act, sh, with_down, skip, lr, cqn, u);
+    Warp::sync();  // j's operations re-read the entries i's operations may have lowered
   }
   if (xpulse_del) {
     if (Warp::lane() == 0) {
@@ -419,6 +556,9 @@ DMD_DEV void partial_events(Rep& r, int i, int j, bool xpulse_del) {
     Warp::sync();
   }
 }
+
+DMD_DEV void partial_events(Rep& r, int i, int j, bool xpulse_del) { partial_events_t<false>(r, i, j, xpulse_del, nullptr, nullptr, nullptr); }
+
 
 // one lane does the whole list of bead l (bulk path: events.f:23-107 with one lane per bead)
 DMD_DEV void redo_lane(Rep& r, int l) {
@@ -716,11 +856,13 @@ DMD_DEV int exch(int32_t* p, int v) {
 #endif
 }
 
-DMD_DEV void cell_build(Rep& r) {
+// (t0, ts): first bead and stride of the calling thread -- (lane, DMD_W) when one warp owns the replica,
+// (thread index, CTA size) when a whole CTA does (dmd_block.h)
+DMD_DEV void cell_build(Rep& r, int t0 = Warp::lane(), int ts = DMD_W) {
   const SysConst& s = *r.c.sys;
   const int ncr = s.ncr, nc = s.num_cell, nw = s.n_wrap;
   Warp::sync();
-  for (int k = Warp::lane(); k < r.N; k += DMD_W) {
+  for (int k = t0; k < r.N; k += ts) {
     int cx, cy, cz;
     cell_coords(s, r.rec[k], cx, cy, cz);
     r.cellof[k] = 1 + (cx + nw) + (cy + nw) * nc + (cz + nw) * nc * nc;  // cell_add.f:25
@@ -735,11 +877,11 @@ DMD_DEV void cell_build(Rep& r) {
   Warp::sync();
 }
 
-DMD_DEV void cell_clear(Rep& r) {
+DMD_DEV void cell_clear(Rep& r, int t0 = Warp::lane(), int ts = DMD_W) {
   const SysConst& s = *r.c.sys;
   const int ncr = s.ncr;
   Warp::sync();
-  for (int k = Warp::lane(); k < r.N; k += DMD_W) {
+  for (int k = t0; k < r.N; k += ts) {
     if (r.cnext[k] == -2) continue;
     int cx, cy, cz;
     cell_coords(s, r.rec[k], cx, cy, cz);
@@ -748,11 +890,12 @@ DMD_DEV void cell_clear(Rep& r) {
   Warp::sync();
 }
 
-DMD_DEV void nbor_build(Rep& r) {
+template <bool PREFETCH>
+DMD_DEV void nbor_build(Rep& r, int t0 = Warp::lane(), int ts = DMD_W) {
   const SysConst& s = *r.c.sys;
   const int ncr = s.ncr, cap = r.cap;
   int overflow = 0;
-  for (int k = Warp::lane(); k < r.N; k += DMD_W) {
+  for (int k = t0; k < r.N; k += ts) {
     const BeadRec rk = r.rec[k];
     const uint32_t mk = r.c.meta[k];
     const int ck = r.c.chain[k];
@@ -760,42 +903,65 @@ DMD_DEV void nbor_build(Rep& r) {
     if (r.cnext[k] != -2) {
       int cx, cy, cz;
       cell_coords(s, rk, cx, cy, cz);
-      for (int dz = -2; dz <= 2; dz++) {
-        int z = cz + dz;
-        z = z < 0 ? z + ncr : (z >= ncr ? z - ncr : z);
-        for (int dy = -2; dy <= 2; dy++) {
-          int y = cy + dy;
-          y = y < 0 ? y + ncr : (y >= ncr ? y - ncr : y);
-          const int rowbase = (y + z * ncr) * ncr;
-          for (int dx = -2; dx <= 2; dx++) {
-            int x = cx + dx;
-            x = x < 0 ? x + ncr : (x >= ncr ? x - ncr : x);
-            for (int j = r.cellhead[rowbase + x]; j >= 0; j = r.cnext[j]) {
-              if (j == k) continue;
-              const int sc = static_code(s, mk, ck, k, r.c.meta[j], r.c.chain[j], j);
-              bool in;
-              if (code_is_bonded_class(sc)) {
-                in = true;  // nbor.f:60
-              } else {
-                const BeadRec rj = r.rec[j];
-                const int code = overlay_code(sc, k, rk, j, rj);
-                double rx = rk.x - rj.x, ry = rk.y - rj.y, rz = rk.z - rj.z;  // nbor.f:97-103
-                rx = rx - dmd_round(rx);
-                ry = ry - dmd_round(ry);
-                rz = rz - dmd_round(rz);
-                double rijsq = rx * rx + ry * ry + rz * rz;
-                in = rijsq <= s.rlsq[code];  // nbor.f:105
-              }
-              if (in) {
-                uint32_t e = ((uint32_t)sc << NB_SHIFT) | (uint32_t)j;
-                if (j > k) {
-                  if (nu < cap) r.up[(size_t)k * cap + nu] = e;
-                  nu++;
-                } else {
-                  if (nd < cap) r.dn[(size_t)k * cap + nd] = e;
-                  nd++;
-                }
-              }
+      // candidate test + list append for bead j found in the stencil of k
+      auto visit = [&](int j) {
+        if (j == k) return;
+        const int sc = static_code(s, mk, ck, k, r.c.meta[j], r.c.chain[j], j);
+        bool in;
+        if (code_is_bonded_class(sc)) {
+          in = true;  // nbor.f:60
+        } else {
+          const BeadRec rj = r.rec[j];
+          const int code = overlay_code(sc, k, rk, j, rj);
+          double rx = rk.x - rj.x, ry = rk.y - rj.y, rz = rk.z - rj.z;  // nbor.f:97-103
+          rx = rx - dmd_round(rx);
+          ry = ry - dmd_round(ry);
+          rz = rz - dmd_round(rz);
+          double rijsq = rx * rx + ry * ry + rz * rz;
+          in = rijsq <= s.rlsq[code];  // nbor.f:105
+        }
+        if (in) {
+          uint32_t e = ((uint32_t)sc << NB_SHIFT) | (uint32_t)j;
+          if (j > k) {
+            if (nu < cap) r.up[(size_t)k * cap + nu] = e;
+            nu++;
+          } else {
+            if (nd < cap) r.dn[(size_t)k * cap + nd] = e;
+            nd++;
+          }
+        }
+      };
+      if (PREFETCH) {
+        // latency-bound caller (one CTA per replica): the 25 heads of a z-plane are loaded together, then walked
+        int xs[5], ys[5];
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+          int x = cx + q - 2, y = cy + q - 2;
+          xs[q] = x < 0 ? x + ncr : (x >= ncr ? x - ncr : x);
+          ys[q] = y < 0 ? y + ncr : (y >= ncr ? y - ncr : y);
+        }
+        for (int dz = -2; dz <= 2; dz++) {
+          int z = cz + dz;
+          z = z < 0 ? z + ncr : (z >= ncr ? z - ncr : z);
+          int heads[25];
+#pragma unroll
+          for (int q = 0; q < 25; q++) heads[q] = r.cellhead[(ys[q / 5] + z * ncr) * ncr + xs[q % 5]];
+#pragma unroll 1
+          for (int q = 0; q < 25; q++)
+            for (int j = heads[q]; j >= 0; j = r.cnext[j]) visit(j);
+        }
+      } else {
+        for (int dz = -2; dz <= 2; dz++) {
+          int z = cz + dz;
+          z = z < 0 ? z + ncr : (z >= ncr ? z - ncr : z);
+          for (int dy = -2; dy <= 2; dy++) {
+            int y = cy + dy;
+            y = y < 0 ? y + ncr : (y >= ncr ? y - ncr : y);
+            const int rowbase = (y + z * ncr) * ncr;
+            for (int dx = -2; dx <= 2; dx++) {
+              int x = cx + dx;
+              x = x < 0 ? x + ncr : (x >= ncr ? x - ncr : x);
+              for (int j = r.cellhead[rowbase + x]; j >= 0; j = r.cnext[j]) visit(j);
             }
           }
         }
@@ -816,7 +982,7 @@ DMD_DEV void nbor_build(Rep& r) {
 
 DMD_DEV void nbor(Rep& r) {  // nbor.f:33-137
   cell_build(r);
-  nbor_build(r);
+  nbor_build<false>(r);
   cell_clear(r);
 }
 
@@ -829,7 +995,7 @@ DMD_COLD void ghost_event_cold(Rep r) {
     i = (int)(rng_uniform(r.seed, r.ctr) * N);
   } while (i == N);
   BeadRec b = r.rec[i];
-  const double bmi = r.c.sys->bmass[b.ident];
+  const double bmi = r.c.hot->bmass[b.ident];
   b.x = b.x + b.vx * r.tfalse;
   b.y = b.y + b.vy * r.tfalse;
   b.z = b.z + b.vz * r.tfalse;
@@ -995,14 +1161,8 @@ DMD_COLD void output_event_cold(Rep r) {
 }
 
 // one iteration of main.F90:484-1258 with serial semantics
-DMD_DEV bool step(Rep& r) {
-  flush_dirty(r);
-  CalEnt ev;
-  const int o = pop_min(r, ev);
-  if (o < 0) {
-    set_error(r, DMD_E_CAL_EMPTY, 0);
-    return false;
-  }
+// process calendar entry o (already popped): main.F90:639-1246
+DMD_DEV void process_one(Rep& r, int o, const CalEnt& ev) {
   r.tfalse = ev.t;
   r.coll += 1;
   if (o < r.N) {
@@ -1017,6 +1177,17 @@ DMD_DEV bool step(Rep& r) {
     r.dirty0 = r.dirty1 = 0;
   }
   r.old_tfalse = r.tfalse;
+}
+
+DMD_DEV bool step(Rep& r) {
+  flush_dirty(r);
+  CalEnt ev;
+  const int o = pop_min(r, ev);
+  if (o < 0) {
+    set_error(r, DMD_E_CAL_EMPTY, 0);
+    return false;
+  }
+  process_one(r, o, ev);
   return r.error == 0;
 }
 
@@ -1077,6 +1248,181 @@ DMD_DEV void sync_positions(Rep& r) {
     p->x = x - dmd_round(x);
     p->y = y - dmd_round(y);
     p->z = z - dmd_round(z);
+  }
+  Warp::sync();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// run start on the device (dmdb_set_state / dmdb_set_state_all): wrap (inputinfo.f:89-91, main.F90:206-208),
+// time constants (main.F90:143-156), per-bead reset (:205-234), restart fix-up from bptnr (:249-321) and the
+// pseudo-event times (:408-423; the ghost time is drawn by the start kernel).  Writes every per-replica array
+// the event loop reads except the neighbour lists, which nbor() builds next.
+//   sv      N x 6 (x,y,z,vx,vy,vz per bead, box units) as uploaded;  bptnr1  N 1-based partners or nullptr
+//   nc      ascending indices of the N and C beads (the only H-bond capable ones), n_nc of them
+// The fix-up is order dependent (identity changes made on the way affect later tests, and a later repuls_add
+// overwrites an earlier one), so it is done in two steps: all lanes collect the pairs the literal k < k_j double
+// loop can act on -- N-C pairs inside their well with ev_code 15 and non-terminal beads, and bonded pairs -- into
+// scratch (the not yet built up-list array), then they are ranked lexicographically and lane 0 replays them.
+// ---------------------------------------------------------------------------------------------------------
+DMD_DEV void init_replica(Rep& r, const double* sv, const int32_t* bptnr1, double tstar, uint64_t seed,
+                          const int32_t* nc, int n_nc, int cal_stride) {
+  const SysConst& s = *r.c.sys;
+  const int N = r.N;
+  r.error = 0;
+  r.error_info = 0;
+  Warp::sync();
+  for (int k = Warp::lane(); k < N; k += DMD_W) {
+    BeadRec b;
+    double x = sv[6 * (size_t)k], y = sv[6 * (size_t)k + 1], z = sv[6 * (size_t)k + 2];
+    x = x - dmd_round(x); y = y - dmd_round(y); z = z - dmd_round(z);  // inputinfo.f:89-91
+    x = x - dmd_round(x); y = y - dmd_round(y); z = z - dmd_round(z);  // main.F90:206-208
+    b.x = x; b.y = y; b.z = z;
+    b.vx = sv[6 * (size_t)k + 3]; b.vy = sv[6 * (size_t)k + 4]; b.vz = sv[6 * (size_t)k + 5];
+    int bp = bptnr1 ? bptnr1[k] - 1 : -1;
+    if (bp < -1 || bp >= N) {
+      bp = -1;
+      r.error = DMD_E_BAD_INPUT;  // reported by the host after the launch
+      r.error_info = k;
+    }
+    b.bptnr = bp;
+    b.er1 = b.er2 = -1;
+    b.ident = (uint8_t)meta_id0(r.c.meta[k]);
+    b.ov1 = b.ov2 = 1;
+    b.pad = 0;
+    r.rec[k] = b;
+    r.er34[2 * k] = -1;
+    r.er34[2 * k + 1] = -1;
+    r.oldr[3 * k] = x; r.oldr[3 * k + 1] = y; r.oldr[3 * k + 2] = z;
+  }
+  {  // an input error seen by any lane
+    const unsigned m = Warp::ballot(r.error != 0);
+    if (m) {
+      const int src = dmd_ffs(m) - 1;
+      r.error = Warp::shfl(r.error, src);
+      r.error_info = Warp::shfl(r.error_info, src);
+    }
+  }
+  Warp::sync();
+  // ---- main.F90:249-321, step 1: collect candidate pairs (k < kj) as pairs of ints in scratch
+  int32_t* hits = reinterpret_cast<int32_t*>(r.up);
+  const int hit_cap = (int)(((size_t)N * r.cap) / 4);  // first half: unsorted, second half: sorted
+  int nh = 0;
+  for (int base = 0; base < n_nc; base += DMD_W) {
+    const int ik = base + Warp::lane();
+    const int k = ik < n_nc ? nc[ik] : -1;
+    BeadRec a;
+    uint32_t mk = 0;
+    int ck = 0;
+    if (k >= 0) {
+      a = r.rec[k];
+      mk = r.c.meta[k];
+      ck = r.c.chain[k];
+    }
+    int ij = ik + 1;
+    while (true) {
+      // next pair of this lane that qualifies
+      bool found = false;
+      int kj = -1;
+      while (k >= 0 && ij < n_nc) {
+        kj = nc[ij];
+        ij++;
+        const BeadRec b = r.rec[kj];
+        bool hit = kj == a.bptnr;
+        if (!hit && a.ident + b.ident == 5) {
+          double rx = a.x - b.x, ry = a.y - b.y, rz = a.z - b.z;
+          rx = rx - dmd_round(rx); ry = ry - dmd_round(ry); rz = rz - dmd_round(rz);
+          const double rijsq = rx * rx + ry * ry + rz * rz;
+          const double diff = rijsq - r.c.tab->welldia_sq[tix(a.ident, b.ident)];
+          const uint32_t mj = r.c.meta[kj];
+          hit = diff < 0.0 && static_code(s, mk, ck, k, mj, r.c.chain[kj], kj) == 15 && !is_terminal_bead(s, mk) &&
+                !is_terminal_bead(s, mj);
+        }
+        if (hit) {
+          found = true;
+          break;
+        }
+      }
+      const unsigned m = Warp::ballot(found);
+      if (!m) break;
+      const int pos = nh + dmd_popc(m & ((1u << Warp::lane()) - 1u));
+      if (found && pos < hit_cap) {
+        hits[2 * pos] = k;
+        hits[2 * pos + 1] = kj;
+      }
+      nh += dmd_popc(m);
+    }
+  }
+  if (nh > hit_cap) {
+    set_error(r, DMD_E_NBR_CAP, nh);
+    nh = 0;
+  }
+  Warp::sync();
+  // ---- step 2: lexicographic rank of every pair, then lane 0 replays them in the literal loop order
+  int32_t* sorted = hits + 2 * (size_t)hit_cap;
+  for (int h = Warp::lane(); h < nh; h += DMD_W) {
+    const int k = hits[2 * h], kj = hits[2 * h + 1];
+    int rank = 0;
+    for (int m = 0; m < nh; m++) {
+      const int k2 = hits[2 * m], kj2 = hits[2 * m + 1];
+      if (k2 < k || (k2 == k && kj2 < kj)) rank++;
+    }
+    sorted[2 * rank] = k;
+    sorted[2 * rank + 1] = kj;
+  }
+  Warp::sync();
+  if (Warp::lane() == 0) {
+    for (int h = 0; h < nh; h++) {
+      const int k = sorted[2 * h], kj = sorted[2 * h + 1];
+      BeadRec* a = &r.rec[k];
+      BeadRec* b = &r.rec[kj];
+      if (a->ident + b->ident == 5) {
+        double rx = a->x - b->x, ry = a->y - b->y, rz = a->z - b->z;
+        rx = rx - dmd_round(rx); ry = ry - dmd_round(ry); rz = rz - dmd_round(rz);
+        const double rijsq = rx * rx + ry * ry + rz * rz;
+        const double diff = rijsq - r.c.tab->welldia_sq[tix(a->ident, b->ident)];
+        const uint32_t mk = r.c.meta[k], mj = r.c.meta[kj];
+        if (diff < 0.0 && static_code(s, mk, r.c.chain[k], k, mj, r.c.chain[kj], kj) == 15 && !is_terminal_bead(s, mk) &&
+            !is_terminal_bead(s, mj)) {
+          if (a->ident == 1) repuls_add(r, k, kj);
+          else repuls_add(r, kj, k);
+        }
+      }
+      if (kj == a->bptnr) {
+        if (a->ident == 1) { a->ident = 5; b->ident = 8; }
+        else { a->ident = 8; b->ident = 5; }
+      }
+    }
+  }
+  Warp::sync();
+  // ---- time constants and tallies (main.F90:127, 143-156), calendar reset (:212-234, 408-423)
+  r.t = 0.0; r.tfalse = 0.0; r.old_tfalse = 0.0;
+  r.setemp = tstar * 12.0;
+  r.t_fact = 0.00005;
+  r.n_forced = 150.0;
+  r.interval = r.t_fact / dmd_sqrt(r.setemp);
+  r.interval_max = r.n_forced * r.interval;
+  r.avegtime = 0.00005 / dmd_sqrt(r.setemp);
+  r.coll = 0;
+  r.seed = seed;
+  r.ctr = 0;
+  r.n_pair_pred = r.n_nbr_visits = 0;
+  r.n_log = r.n_out = 0;
+  if (Warp::lane() == 0) {
+    RepScalars& q = *r.sc;
+    for (int k = 0; k < 32; k++) q.nevents[k] = 0;
+    q.numghosts = q.nupdates = q.nforcedupdate = 0;
+    q.rng_seed = seed;
+  }
+  for (int k = Warp::lane(); k < cal_stride; k += DMD_W) {
+    CalEnt e;
+    e.t = T_PAD; e.ptnr = -1; e.type = -1;
+    if (k < N) e.t = r.interval_max + 1e-10;  // main.F90:212
+    else if (k < N + 3) {
+      e.t = k == N ? 1000000000.0 : (k == N + 1 ? r.interval : 3.3 / (dmd_sqrt(r.setemp)) + 5);  // :416,421,423
+      e.ptnr = -2;
+      e.type = -2;
+    }
+    r.cal[k] = e;
   }
   Warp::sync();
 }

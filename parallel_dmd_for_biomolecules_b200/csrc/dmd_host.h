@@ -1,7 +1,8 @@
 // dmd_host.h -- host-side model set-up of libdmdb200: turns the reference's raw parameter tables and chain
 // topology into the constant blocks the device engine reads.  Replaces (runs once, not on the hot path):
 //   inputinfo.f:105-411 (tables, topology), scale_down.f:27-79, make_code.f:18-66 (ev_param),
-//   nbor_setup.f:13-118 (cut-offs), main.F90:389-396 (cell grid), main.F90:143-156,205-321,408-423 (run start).
+//   nbor_setup.f:13-118 (cut-offs), main.F90:389-396 (cell grid).  The run start itself (main.F90:143-156, 205-321,
+//   408-423) is done on the device by init_replica() in dmd_engine.h.
 #pragma once
 #include <cmath>
 #include <cstring>
@@ -18,19 +19,13 @@ namespace dmd {
 struct HostModel {
   SysConst sys;
   PairTables tab;
+  HotConst hot;
+  std::vector<double> bl;  // nres x 6
   std::vector<uint32_t> meta;
   std::vector<int32_t> chain;
   std::vector<uint8_t> id0;
   std::vector<int32_t> nc_beads;  // indices of the N and C beads (ascending): the only H-bond capable ones
   dmdb_params params;
-};
-
-struct HostReplicaInit {  // everything dmdb_set_state uploads for one replica
-  std::vector<BeadRec> rec;
-  std::vector<int32_t> er34;
-  std::vector<double> oldr;
-  std::vector<CalEnt> cal;     // cal_stride entries (padding t = 1e300)
-  RepScalars scal;
 };
 
 inline double hsq(double x) { return x * x; }
@@ -244,107 +239,21 @@ inline void build_model(const dmdb_params& p, const dmdb_topology& topo, const d
   if (s.ncr < 5) throw std::runtime_error("box too small: fewer than 5 real cells per dimension");
   s.width = boxl / (double)(s.num_cell - 2 * s.n_wrap);
   s.half = boxl / 2.0;
-}
-
-// main.F90:127,143-156: time constants of a run at temperature tstar
-inline void init_scalars(RepScalars& q, double tstar, uint64_t seed) {
-  std::memset(&q, 0, sizeof(q));
-  q.setemp = tstar * 12.0;                       // main.F90:127
-  q.t_fact = 0.00005;                            // main.F90:144
-  q.n_forced = 150.0;
-  q.interval = q.t_fact / std::sqrt(q.setemp);
-  q.interval_max = q.n_forced * q.interval;
-  q.avegtime = 0.00005 / std::sqrt(q.setemp);    // main.F90:156
-  q.rng_seed = seed;
-}
-
-// main.F90:212-234, 408-423: every bead at interval_max + ltstep, pseudo-events armed
-inline void init_calendar(const SysConst& s, const RepScalars& q, int cal_stride, std::vector<CalEnt>& cal) {
-  const int N = s.N;
-  CalEnt pad;
-  pad.t = 1e300; pad.ptnr = -1; pad.type = -1;
-  cal.assign(cal_stride, pad);
-  for (int k = 0; k < N; k++) cal[k].t = q.interval_max + 1e-10;  // main.F90:212
-  cal[N].t = 1000000000.0;                       // ghost: drawn on the device when canon (main.F90:408-416)
-  cal[N + 1].t = q.interval;                     // main.F90:421
-  cal[N + 2].t = 3.3 / (std::sqrt(q.setemp)) + 5;  // main.F90:423
-  for (int k = N; k < N + 3; k++) { cal[k].ptnr = -2; cal[k].type = -2; }
-}
-
-inline void host_set_pair_code(std::vector<BeadRec>& rec, int a, int b, int code) {
-  if (rec[a].er1 == b) rec[a].ov1 = (uint8_t)code;
-  if (rec[a].er2 == b) rec[a].ov2 = (uint8_t)code;
-  if (rec[b].er1 == a) rec[b].ov1 = (uint8_t)ov_mirror(code);
-  if (rec[b].er2 == a) rec[b].ov2 = (uint8_t)ov_mirror(code);
-}
-
-// repuls_add.f:14-47 on host arrays (restart fix-up only)
-inline void host_repuls_add(const HostModel& m, HostReplicaInit& h, int n, int cb) {
-  const SysConst& s = m.sys;
-  const int Ln = s.chnln[meta_sp(m.meta[n])], Lc = s.chnln[meta_sp(m.meta[cb])];
-  const int ncim1 = n + Ln - 1, ncai = n - Ln, ncaj = cb - 2 * Lc, nnjp1 = cb - Lc + 1;
-  h.rec[n].er1 = ncaj; h.rec[n].er2 = nnjp1; h.rec[cb].er1 = ncai; h.rec[cb].er2 = ncim1;
-  h.rec[n].ov1 = h.rec[n].ov2 = h.rec[cb].ov1 = h.rec[cb].ov2 = 1;
-  host_set_pair_code(h.rec, n, ncaj, 40);
-  host_set_pair_code(h.rec, n, nnjp1, 40);
-  host_set_pair_code(h.rec, cb, ncai, 40);
-  host_set_pair_code(h.rec, cb, ncim1, 40);
-  h.er34[2 * ncaj] = n; h.er34[2 * nnjp1] = n; h.er34[2 * ncai] = cb; h.er34[2 * ncim1] = cb;
-  h.er34[2 * n + 1] = cb; h.er34[2 * cb + 1] = n;
-}
-
-// run start for one replica: inputinfo.f:89-91 (wrap), main.F90:143-156 (time constants), :205-234 (reset),
-// :241-321 (restart fix-up from bptnr), :408-423 (pseudo-event times; the ghost time is drawn on the device).
-inline void build_replica_init(const HostModel& m, const double* sv, const int32_t* bptnr1, double tstar, uint64_t seed,
-                               int cal_stride, HostReplicaInit& h) {
-  const SysConst& s = m.sys;
-  const int N = s.N;
-  h.rec.assign(N, BeadRec());
-  h.er34.assign(2 * (size_t)N, -1);
-  h.oldr.assign(3 * (size_t)N, 0.0);
-  for (int k = 0; k < N; k++) {
-    BeadRec& b = h.rec[k];
-    double x = sv[6 * (size_t)k], y = sv[6 * (size_t)k + 1], z = sv[6 * (size_t)k + 2];
-    x = x - std::round(x); y = y - std::round(y); z = z - std::round(z);  // inputinfo.f:89-91
-    x = x - std::round(x); y = y - std::round(y); z = z - std::round(z);  // main.F90:206-208
-    b.x = x; b.y = y; b.z = z;
-    b.vx = sv[6 * (size_t)k + 3]; b.vy = sv[6 * (size_t)k + 4]; b.vz = sv[6 * (size_t)k + 5];
-    b.bptnr = bptnr1 ? bptnr1[k] - 1 : -1;
-    if (b.bptnr < -1 || b.bptnr >= N) throw std::runtime_error("bptnr entry out of range");
-    b.er1 = b.er2 = -1;
-    b.ident = m.id0[k];
-    b.ov1 = b.ov2 = 1;
-    b.pad = 0;
-    h.oldr[3 * (size_t)k] = x; h.oldr[3 * (size_t)k + 1] = y; h.oldr[3 * (size_t)k + 2] = z;
-  }
-  // main.F90:249-321, literal pair order (identity changes made on the way affect later tests)
-  // (only N / C beads can satisfy either test, so the literal k < k_j double loop is restricted to them)
-  const std::vector<int32_t>& nc = m.nc_beads;
-  for (size_t ik = 0; ik < nc.size(); ik++) {
-    const int k = nc[ik];
-    for (size_t ij = ik + 1; ij < nc.size(); ij++) {
-      const int kj = nc[ij];
-      BeadRec& a = h.rec[k];
-      BeadRec& b = h.rec[kj];
-      if (a.ident + b.ident == 5) {
-        double rx = a.x - b.x, ry = a.y - b.y, rz = a.z - b.z;
-        rx = rx - std::round(rx); ry = ry - std::round(ry); rz = rz - std::round(rz);
-        double rijsq = rx * rx + ry * ry + rz * rz;
-        double diff = rijsq - m.tab.welldia_sq[(a.ident - 1) * 28 + (b.ident - 1)];
-        if (diff < 0.0 && static_code(s, m.meta[k], m.chain[k], k, m.meta[kj], m.chain[kj], kj) == 15 &&
-            !is_terminal_bead(s, m.meta[k]) && !is_terminal_bead(s, m.meta[kj])) {
-          if (a.ident == 1) host_repuls_add(m, h, k, kj);
-          else host_repuls_add(m, h, kj, k);
-        }
-      }
-      if (kj == a.bptnr) {
-        if (a.ident == 1) { a.ident = 5; b.ident = 8; }
-        else { a.ident = 8; b.ident = 5; }
-      }
+  // ---- the hot copies (HotConst + per-residue bond windows)
+  std::memset(&m.hot, 0, sizeof(m.hot));
+  std::memcpy(m.hot.ev_param1, s.ev_param1, sizeof(s.ev_param1));
+  std::memcpy(m.hot.ev_param2, s.ev_param2, sizeof(s.ev_param2));
+  std::memcpy(m.hot.ev_param3, s.ev_param3, sizeof(s.ev_param3));
+  std::memcpy(m.hot.sqz610, s.sqz610, sizeof(s.sqz610));
+  std::memcpy(m.hot.bmass, s.bmass, sizeof(s.bmass));
+  m.hot.chnln0 = s.chnln[0];
+  m.hot.nres = s.chnln[0] + (topo.n_species == 2 ? s.chnln[1] : 0);
+  m.bl.assign((size_t)m.hot.nres * 6, 0.0);
+  for (int x = 0; x < m.hot.nres; x++)
+    for (int kind = 0; kind < 3; kind++) {
+      m.bl[(size_t)x * 6 + 2 * kind] = s.blmin_sc[kind][x];
+      m.bl[(size_t)x * 6 + 2 * kind + 1] = s.blmax_sc[kind][x];
     }
-  }
-  init_scalars(h.scal, tstar, seed);
-  init_calendar(s, h.scal, cal_stride, h.cal);
 }
 
 }  // namespace dmd

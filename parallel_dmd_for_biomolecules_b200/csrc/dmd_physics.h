@@ -13,8 +13,10 @@ constexpr double SMDIST = 5e-12;   // def.h:2
 constexpr double T_NONE = 1000000000.0;  // events.f:28
 
 struct Ctx {                 // read-only context of one warp
-  const SysConst* sys;       // global memory (L2-resident, tiny)
+  const SysConst* sys;       // global memory (cold fields only)
   const PairTables* tab;     // shared-memory copy of the 28x28 tables
+  const HotConst* hot;       // shared-memory copy of the squeeze factors, bond windows of codes 4-9, masses
+  const double* bl;          // per-residue side-chain bond windows (shared memory when nres <= HOT_MAX_RES)
   const uint32_t* meta;
   const int32_t* chain;
 };
@@ -44,22 +46,22 @@ DMD_DEV Geom pair_geom(const BeadRec& a, const BeadRec& b, double tfalse) {
 // lower-index (backbone) bead.
 DMD_DEV void bond_limits(const Ctx& c, int code, uint32_t mi, double& blmin, double& blmax) {
   if (code >= 10) {
-    int r = (meta_sp(mi) ? c.sys->chnln[0] : 0) + meta_res(mi) - 1;
-    blmin = c.sys->blmin_sc[code - 10][r];
-    blmax = c.sys->blmax_sc[code - 10][r];
+    const int r = (meta_sp(mi) ? c.hot->chnln0 : 0) + meta_res(mi) - 1;
+    blmin = c.bl[r * 6 + 2 * (code - 10)];
+    blmax = c.bl[r * 6 + 2 * (code - 10) + 1];
   } else {
-    blmin = c.sys->ev_param2[code];
-    blmax = c.sys->ev_param3[code];
+    blmin = c.hot->ev_param2[code];
+    blmax = c.hot->ev_param3[code];
   }
 }
 
 // hard-core diameter^2 of core.f:27-31 / eventdyn.f:70-74 / checkover.f:38-42
 DMD_DEV double core_sigsq(const Ctx& c, int code, int idi, int idj) {
-  double f = c.sys->ev_param1[code];
+  double f = c.hot->ev_param1[code];
   double sigsq = c.tab->sigma_sq[tix(idi, idj)] * (f * f);
   if (code >= 22 && code <= 26) {
     int k = idi > idj ? idi : idj;
-    double q = c.sys->sqz610[(code - 22) * 29 + k];
+    double q = c.hot->sqz610[(code - 22) * 29 + k];
     sigsq = sigsq * (q * q);
   }
   return sigsq;
@@ -109,7 +111,7 @@ DMD_DEV void pair_time_core(const Ctx& c, int code, double bij, double rijsq, do
         t_leave = 16;
         t_enter = 7;
       } else if (bonded) {  // bound to each other: core at the 1.05*(2.24 A) factor, exit 8, no inside test
-        const double f = c.sys->ev_param1[15];
+        const double f = c.hot->ev_param1[15];
         R1sq = sig * f * f;
         t_leave = 8;
         inside_force = 1;
@@ -190,7 +192,7 @@ DMD_DEV int event_dynamics(const Ctx& c, int ct, int code, BeadRec& a, BeadRec& 
   const Geom g = pair_geom(a, b, tfalse);
   const double rxij = g.rx, ryij = g.ry, rzij = g.rz, bij = g.bij;
   const int idi = a.ident, idj = b.ident;
-  const double bmi = c.sys->bmass[idi], bmj = c.sys->bmass[idj];
+  const double bmi = c.hot->bmass[idi], bmj = c.hot->bmass[idj];
   const double rmass = 2 * bmi * bmj / (bmi + bmj);
   double ratio = 0.0, bumpdist = 0.0, sgn = 0.0;  // sgn +1: a += bump*r, b -= ; -1: the opposite
   if (ct == 2 || ct == 3) {
@@ -200,7 +202,7 @@ DMD_DEV int event_dynamics(const Ctx& c, int ct, int code, BeadRec& a, BeadRec& 
   } else if (ct == 1) {
     double sigsq;
     if (code == 15) {
-      double f = c.sys->ev_param1[15];
+      double f = c.hot->ev_param1[15];
       sigsq = bonded ? c.tab->sigma_sq[tix(idi, idj)] * (f * f) : c.tab->sigma_sq[tix(idi, idj)];
     } else {
       sigsq = core_sigsq(c, code, idi, idj);
@@ -292,13 +294,13 @@ DMD_DEV int event_dynamics_hot(const Ctx& c, int ct, int code, BeadRec& a, BeadR
   const Geom g = pair_geom(a, b, tfalse);
   const double rxij = g.rx, ryij = g.ry, rzij = g.rz, bij = g.bij;
   const int idi = a.ident, idj = b.ident;
-  const double bmi = c.sys->bmass[idi], bmj = c.sys->bmass[idj];
+  const double bmi = c.hot->bmass[idi], bmj = c.hot->bmass[idj];
   const double rmass = 2 * bmi * bmj / (bmi + bmj);
   double ratio;
   if (ct == 1) {
     double sigsq;
     if (code == 15) {
-      double f = c.sys->ev_param1[15];
+      double f = c.hot->ev_param1[15];
       sigsq = bonded ? c.tab->sigma_sq[tix(idi, idj)] * (f * f) : c.tab->sigma_sq[tix(idi, idj)];
     } else {
       sigsq = core_sigsq(c, code, idi, idj);

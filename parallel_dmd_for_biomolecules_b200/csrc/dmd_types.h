@@ -62,6 +62,18 @@ struct PairTables {
   double ep_sqrt[784];
 };
 
+// the constants every pair prediction / collision reads (a copy of the SysConst fields of the same name): staged
+// into shared memory next to the pair tables so that the hot loop never goes to L2 for a squeeze factor or a mass
+constexpr int HOT_MAX_RES = 64;  // per-residue bond windows staged in shared memory up to this many residues
+struct HotConst {
+  double ev_param1[51];
+  double ev_param2[51];
+  double ev_param3[51];
+  double sqz610[5 * 29];
+  double bmass[29];
+  int32_t chnln0, nres;
+};
+
 // everything that is constant during a run and identical for all replicas
 struct SysConst {
   int32_t N;                 // beads per replica
@@ -107,6 +119,7 @@ constexpr int DMD_E_NBR_CAP = 1;    // neighbour list capacity exceeded
 constexpr int DMD_E_CAL_EMPTY = 2;  // calendar has no finite entry
 constexpr int DMD_E_NEG_TIME = 3;   // tij < -1e-10 (events.f:59-73 debugging guard)
 constexpr int DMD_E_GRID = 4;       // bead outside the cell grid
+constexpr int DMD_E_BAD_INPUT = 5;  // bptnr entry out of range (run start)
 
 // one calendar entry: tim(k), nptnr(k), coltype(k) of header.f:20-22,47 side by side so that popping the
 // minimum delivers the whole event in one access.  type: low 8 bits coltype (as int8), bits 8-15 the static
@@ -134,6 +147,9 @@ struct DevArrays {
   // shared by all replicas
   const SysConst* sys;
   const PairTables* tables;
+  const HotConst* hot;
+  const int32_t* nc_beads;  // ascending indices of the N and C beads (run-start fix-up, main.F90:249-321)
+  const double* bl;       // nres x 6: per-residue side-chain bond windows (min,max of codes 10, 11, 12), bond.f:82-91
   const uint32_t* meta;   // N
   const int32_t* chain;   // N (global chain index)
   // per replica
@@ -152,8 +168,12 @@ struct DevArrays {
   RepScalars* scal;       // 1
   EventLogRec* log;       // log_cap
   OutRec* out;            // out_cap
+  long long* blkstat;     // 8: batching statistics of the CTA-per-replica engine (dmd_block.h)
   int32_t n_replicas;
   int32_t cal_stride;     // ngroups*32
+  int32_t n_beads;        // N (host-side copy of sys->N)
+  int32_t nres;           // residues over both species (rows of bl)
+  int32_t n_nc;           // entries of nc_beads
 };
 
 }  // namespace dmd

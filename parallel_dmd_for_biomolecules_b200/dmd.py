@@ -27,7 +27,7 @@ SYMBOLS = [
     "dmdb_set_temperature", "dmdb_nbor", "dmdb_predict_all", "dmdb_run", "dmdb_sync_positions", "dmdb_get_cells",
     "dmdb_get_nbors", "dmdb_get_calendar", "dmdb_get_state", "dmdb_get_evcode", "dmdb_energy_of",
     "dmdb_get_event_log", "dmdb_get_replica_stats", "dmdb_potential_energies", "dmdb_set_state_all",
-    "dmdb_get_state_all", "dmdb_apply_temperatures",
+    "dmdb_get_state_all", "dmdb_apply_temperatures", "dmdb_get_batch_stats",
 ]
 
 
@@ -207,6 +207,13 @@ class DMD:
         self._chk(self._l.dmdb_get_event_log(self._h, replica, C.c_int64(first), C.c_int64(n),
                                              out.ctypes.data_as(C.POINTER(Event)), C.byref(n_out)))
         return out[: n_out.value]
+
+    def batch_stats(self, replica=-1) -> dict:
+        """batching statistics of the CTA-per-replica engine (engine=2)"""
+        out = (C.c_int64 * 16)()
+        self._chk(self._l.dmdb_get_batch_stats(self._h, replica, out))
+        return dict(rounds=out[0], executed=out[1], rolled_back=out[2], conflicts=out[3], serial=out[4],
+                    cycles=dict(zip(("scan", "select_sort", "claim", "check", "exec", "commit", "serial"), list(out)[8:15])))
 
     def stats(self, replica=-1) -> Stats:
         s = Stats()

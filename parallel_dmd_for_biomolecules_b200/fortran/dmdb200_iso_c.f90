@@ -21,7 +21,7 @@ module dmdb200
   public :: dmdb_nbor, dmdb_predict_all, dmdb_run, dmdb_sync_positions
   public :: dmdb_get_cells, dmdb_get_nbors, dmdb_get_calendar, dmdb_get_state, dmdb_get_evcode
   public :: dmdb_energy_of, dmdb_get_event_log, dmdb_get_replica_stats
-  public :: dmdb_potential_energies, dmdb_apply_temperatures
+  public :: dmdb_potential_energies, dmdb_apply_temperatures, dmdb_get_batch_stats
   public :: dmdb_error_message
   public :: DMDB_OK, DMDB_ERR_ARG, DMDB_ERR_NO_DEVICE, DMDB_ERR_CUDA, DMDB_ERR_STATE, DMDB_ERR_CAPACITY, &
             DMDB_ERR_PHYSICS, DMDB_MAX_SPECIES
@@ -55,7 +55,7 @@ module dmdb200
   ! the two stdin numbers (main.F90:126-128), the box length (inputinfo.f:78) and the -D behaviour flags
   type, bind(C) :: dmdb_params
     real(c_double) :: boxl, tstar
-    integer(c_int32_t) :: canon, no_hbs, n_wrap, n_replicas, device, nbr_capacity, log_capacity, reserved
+    integer(c_int32_t) :: canon, no_hbs, n_wrap, n_replicas, device, nbr_capacity, log_capacity, engine
     integer(c_int64_t) :: seed   ! uint64_t in C; same bits
   end type
 
@@ -224,6 +224,13 @@ module dmdb200
       type(c_ptr), value :: handle
       integer(c_int), value :: replica
       type(dmdb_stats), intent(out) :: s
+      integer(c_int) :: rc
+    end function
+    function dmdb_get_batch_stats(handle, replica, out) bind(C, name="dmdb_get_batch_stats") result(rc)
+      import :: c_ptr, c_int, c_int64_t
+      type(c_ptr), value :: handle
+      integer(c_int), value :: replica
+      integer(c_int64_t), intent(out) :: out(16)
       integer(c_int) :: rc
     end function
     function dmdb_potential_energies(handle, epot, tstar) bind(C, name="dmdb_potential_energies") result(rc)

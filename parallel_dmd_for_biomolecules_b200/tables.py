@@ -59,7 +59,7 @@ class Params(C.Structure):
         ("device", C.c_int32),
         ("nbr_capacity", C.c_int32),
         ("log_capacity", C.c_int32),
-        ("reserved", C.c_int32),
+        ("engine", C.c_int32),
         ("seed", C.c_uint64),
     ]
 
@@ -278,11 +278,11 @@ def load_default_tables() -> Tables:
 
 
 def make_params(boxl=158.54, tstar=0.18, canon=True, no_hbs=False, n_wrap=2, n_replicas=1, device=0,
-                nbr_capacity=0, log_capacity=0, seed=1058472402) -> Params:
+                nbr_capacity=0, log_capacity=0, seed=1058472402, engine=0) -> Params:
     p = Params()
     p.boxl, p.tstar = boxl, tstar
     p.canon, p.no_hbs, p.n_wrap = int(canon), int(no_hbs), n_wrap
     p.n_replicas, p.device = n_replicas, device
-    p.nbr_capacity, p.log_capacity, p.reserved = nbr_capacity, log_capacity, 0
+    p.nbr_capacity, p.log_capacity, p.engine = nbr_capacity, log_capacity, engine
     p.seed = seed
     return p

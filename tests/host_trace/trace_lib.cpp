@@ -10,8 +10,78 @@
 #include <stdexcept>
 #include <string>
 
+#include <pthread.h>
+
+#include <thread>
+#include <vector>
+
+#include "../../parallel_dmd_for_biomolecules_b200/csrc/dmd_block.h"
 #include "../../parallel_dmd_for_biomolecules_b200/csrc/dmd_engine.h"
 #include "../../parallel_dmd_for_biomolecules_b200/csrc/dmd_types.h"
+
+// The CTA-per-replica engine (dmd_block.h) is emulated with one host thread per (1-lane) virtual warp; its
+// __syncthreads() becomes a pthread barrier, so claims, validation and rollback run with real concurrency.
+namespace dmd {
+static thread_local pthread_barrier_t* g_blk_barrier = nullptr;
+void blk_sync() { pthread_barrier_wait(g_blk_barrier); }
+
+static int trace_block_warps() {
+  const char* e = std::getenv("DMDB_TRACE_WARPS");
+  int n = e ? std::atoi(e) : 8;
+  return n < 1 ? 1 : (n > BK_MAXW ? BK_MAXW : n);
+}
+
+static void trace_run_block(const DevArrays& d, int rid, long long n_events) {
+  const int nw = trace_block_warps();
+  const int N = d.sys->N;
+  BlkShared* S = new BlkShared();
+  std::memset(S, 0, sizeof(*S));
+  std::vector<uint32_t> claim(N + 3, CLAIM_FREE);
+  std::vector<int32_t> cq((size_t)nw * CQ_CAP);
+  pthread_barrier_t bar;
+  pthread_barrier_init(&bar, nullptr, nw);
+  {
+    Rep r0;
+    rep_bind(r0, d, staged_global(d), cq.data(), rid);
+    S->coll = r0.coll;
+    S->target = r0.coll + n_events;
+    S->window = r0.interval * 0.02;
+    S->tlast = -1.0;
+    S->error = r0.error;
+    S->error_info = r0.error_info;
+  }
+  std::vector<std::thread> th;
+  for (int w = 0; w < nw; w++)
+    th.emplace_back([&, w]() {
+      g_blk_barrier = &bar;
+      Rep r;
+      rep_bind(r, d, staged_global(d), cq.data() + (size_t)w * CQ_CAP, rid);
+      if (w != 0) r.n_pair_pred = r.n_nbr_visits = 0;
+      blk_run(*S, r, claim.data(), w, nw);
+      if (w != 0) {
+        blk_atomic_add64(&S->n_pair_pred, r.n_pair_pred);
+        blk_atomic_add64(&S->n_nbr_visits, r.n_nbr_visits);
+      }
+      blk_sync();
+      if (w == 0) {
+        r.n_pair_pred += S->n_pair_pred;
+        r.n_nbr_visits += S->n_nbr_visits;
+        if (S->error && !r.error) {
+          r.error = S->error;
+          r.error_info = S->error_info;
+        }
+        rep_save(r);
+        rebuild_all_groups(r);
+        for (int q = 0; q < 32; q++) r.sc->nevents[q] += S->nevents[q];
+        long long* st = d.blkstat + (size_t)rid * 16;
+        st[0] += S->st_rounds; st[1] += S->st_exec; st[2] += S->st_rollback; st[3] += S->st_conflict; st[4] += S->st_cold;
+      }
+    });
+  for (auto& t : th) t.join();
+  pthread_barrier_destroy(&bar);
+  delete S;
+}
+}  // namespace dmd
 
 namespace be {
 inline bool init(int, std::string&) { return true; }
@@ -22,6 +92,29 @@ inline void d2h(void* h, const void* d, size_t n) { std::memcpy(h, d, n); }
 inline void zero(void* d, size_t n) { std::memset(d, 0, n); }
 inline void fill_i32(int32_t* d, int v, size_t n) {
   for (size_t k = 0; k < n; k++) d[k] = v;
+}
+inline bool block_engine_fits(const dmd::SysConst&) { return true; }
+inline void run_init(const dmd::DevArrays& d, int r0, int nrep, const double* sv, size_t sv_stride, const int32_t* bp,
+                     size_t bp_stride, const double* tstar, unsigned long long seed0) {
+  using namespace dmd;
+  for (int rid = r0; rid < r0 + nrep; rid++) {
+    Rep r;
+    int32_t cq[CQ_CAP];
+    rep_bind(r, d, staged_global(d), cq, rid);
+    const size_t k = (size_t)(rid - r0);
+    init_replica(r, sv + k * sv_stride, bp ? bp + k * bp_stride : nullptr, tstar[rid], seed0 + (unsigned long long)rid,
+                 d.nc_beads, d.n_nc, d.cal_stride);
+    rep_save(r);
+  }
+}
+inline void run_pack(const dmd::DevArrays& d, double* sv, int32_t* bp) {
+  const size_t n = (size_t)d.n_replicas * d.n_beads;
+  for (size_t k = 0; k < n; k++) {
+    const dmd::BeadRec b = d.rec[k];
+    double* o = sv + 6 * k;
+    o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.vx; o[4] = b.vy; o[5] = b.vz;
+    bp[k] = b.bptnr + 1;
+  }
 }
 inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long arg, int32_t* ibuf, dmd::OutRec* eout,
                    double* ms, int* launches) {
@@ -38,7 +131,7 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
     for (int rid = r0; rid < r0 + nrep; rid++) {
       Rep r;
       int32_t cq[CQ_CAP];
-      rep_bind(r, d, d.tables, cq, rid);
+      rep_bind(r, d, staged_global(d), cq, rid);
       switch (op) {
         case 0:
           if (d.sys->canon) {
@@ -53,6 +146,7 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
         case 1: nbor(r); rep_save(r); break;
         case 2: predict_all(r); rep_save(r); break;
         case 3: if (r.error == 0) run_events(r, arg); rep_save(r); break;
+        case 8: if (r.error == 0) trace_run_block(d, rid, arg); break;
         case 4: sync_positions(r); break;
         case 5: { OutRec o; energy_of(r, o); eout[rid] = o; } break;
         case 7: { double tn = ((const double*)ibuf)[rid]; if (tn > 0.0) { retemp(r, tn); rep_save(r); } } break;

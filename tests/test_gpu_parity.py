@@ -22,10 +22,12 @@ def _pair(p, topo, tab, sv, bptnr=None):
     return ora, dev
 
 
+@pytest.mark.parametrize("engine", [1, 2])  # 1 = warp per replica, 2 = CTA per replica with batched commit
 @pytest.mark.parametrize("which,canon,n_events", [("A", False, 20000), ("A", True, 50000), ("B", False, 20000), ("B", True, 100000)])
-def test_event_sequence_matches_oracle(tab, system_a, system_b, which, canon, n_events):
+def test_event_sequence_matches_oracle(tab, system_a, system_b, which, canon, n_events, engine):
     topo, sv, boxl = system_a if which == "A" else system_b
-    p = tables.make_params(boxl=boxl, tstar=0.5 if which == "A" else 0.18, canon=canon, n_replicas=5, log_capacity=n_events)
+    p = tables.make_params(boxl=boxl, tstar=0.5 if which == "A" else 0.18, canon=canon, n_replicas=5, log_capacity=n_events,
+                           engine=engine)
     ora, dev = _pair(p, topo, tab, sv)
     compare_engines(ora, dev, replica=0, n_events=n_events)
     ea, eb = ora.energy(), dev.energy(0)
@@ -45,10 +47,11 @@ def test_event_sequence_matches_oracle(tab, system_a, system_b, which, canon, n_
         assert np.array_equal(dev.state(0)["sv"], dev.state(4)["sv"])
 
 
-def test_hbond_rich_trajectory_and_restart(tab):
+@pytest.mark.parametrize("engine", [1, 2])
+def test_hbond_rich_trajectory_and_restart(tab, engine):
     topo, sv = genconfig.generate_box(["AAAAAAAAAAAA"], [8], 45.0, 0.10, tab, seed=1)
     n = 600000
-    p = tables.make_params(boxl=45.0, tstar=0.10, canon=True, n_replicas=2, log_capacity=n, seed=11)
+    p = tables.make_params(boxl=45.0, tstar=0.10, canon=True, n_replicas=2, log_capacity=n, seed=11, engine=engine)
     ora, dev = _pair(p, topo, tab, sv)
     compare_engines(ora, dev, n_events=n)
     st = ora.stats()
@@ -56,7 +59,7 @@ def test_hbond_rich_trajectory_and_restart(tab):
     ora.sync_positions()
     s = ora.state()
     assert (s["bptnr"] > 0).sum() >= 2
-    p2 = tables.make_params(boxl=45.0, tstar=0.10, canon=True, n_replicas=1, log_capacity=20000, seed=12)
+    p2 = tables.make_params(boxl=45.0, tstar=0.10, canon=True, n_replicas=1, log_capacity=20000, seed=12, engine=engine)
     ora2, dev2 = _pair(p2, topo, tab, s["sv"], bptnr=s["bptnr"])
     assert np.array_equal(ora2.state()["identity"], dev2.state()["identity"])
     assert np.array_equal(ora2.state()["extra_repuls"], dev2.state()["extra_repuls"])
@@ -78,6 +81,27 @@ def test_static_evcode_function_equals_literal_matrix(tab):
         got = dev.evcode(ii[mask], jj[mask])
         overlay = got >= 40
         assert np.array_equal(got[~overlay], m[mask][~overlay])
+
+
+def test_engines_alternate_on_one_handle(tab, system_b):
+    """Both engines work on the same resident state: chunks run alternately by the CTA-per-replica engine and the
+    warp-per-replica engine give the oracle's sequence, and the batching statistics show real batches."""
+    topo, sv, boxl = system_b
+    n = 60000
+    mk = lambda e: tables.make_params(boxl=boxl, tstar=0.18, canon=True, n_replicas=2, log_capacity=n, engine=e)
+    ora = OracleDMD(mk(0), topo, tab)
+    ora.set_state(sv)
+    ora.run(n)
+    dev = DMD(mk(2), topo, tab)
+    dev.set_state(sv)
+    dev.run(n)
+    st = dev.batch_stats(0)
+    assert st["rounds"] > 0 and (n - st["serial"]) / st["rounds"] > 3.0, st  # several events committed per round
+    assert st["executed"] - st["rolled_back"] + st["serial"] == n
+    la, lb = ora.event_log(), dev.event_log(0)
+    for f in ("i", "j", "type", "evcode", "t"):
+        assert np.array_equal(la[f], lb[f]), f
+    assert np.array_equal(ora.state()["sv"], dev.state(0)["sv"])
 
 
 def test_retemp_and_distinct_states(tab, system_b):

@@ -14,7 +14,7 @@ warm = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
 nev = int(sys.argv[3]) if len(sys.argv) > 3 else 3000
 tab = tables.load_default_tables()
 topo, sv = genconfig.system_b(tab, 0.18, seed=1)
-p = tables.make_params(boxl=158.54, tstar=0.18, canon=True, n_replicas=R)
+p = tables.make_params(boxl=158.54, tstar=0.18, canon=True, n_replicas=R, engine=int(os.environ.get('DMDB_ENGINE', '1')))
 d = DMD(p, topo, tab, lib_path=os.environ.get('DMDB_LIB'))
 d.set_state(sv)
 d.run(warm)
