@@ -4,9 +4,9 @@
 //   dmd_event_loop_kernel    the persistent event loop, main.F90:484-1258 (dmdb_run, engine 1: warp per replica)
 //   dmd_block_loop_kernel    the same loop with one CTA per replica, state in shared memory, batched
 //                            conservative commit of independent events (dmdb_run, engine 2; dmd_block.h)
-//   dmd_start_kernel         run start: first ghost time (main.F90:408-416) + nbor() + events()
-//   dmd_nbor_kernel          cell_add.f + nbor.f  (dmdb_nbor)
-//   dmd_predict_all_kernel   events.f             (dmdb_predict_all)
+//   dmd_bulk_*_kernel        grid-parallel, one thread per bead, any system size: run start (init, fix-up of
+//                            main.F90:249-321 through the cell grid), cell_add.f, nbor.f, events.f, group minima
+//                            (dmdb_set_state*, dmdb_nbor, dmdb_predict_all)
 //   dmd_sync_positions_kernel main.F90:1288-1295
 //   dmd_energy_kernel        energy.f
 //   dmd_retemp_kernel        replica-exchange temperature change on resident state (new functionality)
@@ -218,45 +218,6 @@ __global__ void __launch_bounds__(BK_MAXW * 32, 1) dmd_block_loop_kernel(DevArra
   }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_start_kernel(DevArrays d, int r0, int nrep) {
-  __shared__ SmemConsts sconst;
-  const Staged tab = stage_consts(d, &sconst);
-  int rid = replica_of_warp(r0, nrep);
-  if (rid < 0) return;
-  Rep r;
-  rep_bind(r, d, tab, warp_queue(), rid);
-  if (d.sys->canon) {  // main.F90:408-416
-    double tgho = 0.0;
-    while (tgho < 1e-18 || tgho == 1.0) tgho = rng_uniform(r.seed, r.ctr);
-    if (Warp::lane() == 0) r.cal[r.N].t = -1.0 * dmd_log(tgho) * r.avegtime * .0000001;
-  }
-  nbor(r);
-  predict_all(r);
-  rep_save(r);
-}
-
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_nbor_kernel(DevArrays d, int r0, int nrep) {
-  __shared__ SmemConsts sconst;
-  const Staged tab = stage_consts(d, &sconst);
-  int rid = replica_of_warp(r0, nrep);
-  if (rid < 0) return;
-  Rep r;
-  rep_bind(r, d, tab, warp_queue(), rid);
-  nbor(r);
-  rep_save(r);
-}
-
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_predict_all_kernel(DevArrays d, int r0, int nrep) {
-  __shared__ SmemConsts sconst;
-  const Staged tab = stage_consts(d, &sconst);
-  int rid = replica_of_warp(r0, nrep);
-  if (rid < 0) return;
-  Rep r;
-  rep_bind(r, d, tab, warp_queue(), rid);
-  predict_all(r);
-  rep_save(r);
-}
-
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_sync_positions_kernel(DevArrays d, int r0, int nrep) {
   int rid = replica_of_warp(r0, nrep);
   if (rid < 0) return;
@@ -290,20 +251,150 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_retemp_kernel(DevArray
   rep_save(r);
 }
 
-// run start on the device: raw sv / bptnr (staged by dmdb_set_state*) -> every per-replica array
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_init_kernel(DevArrays d, int r0, int nrep, const double* sv,
-                                                                      size_t sv_stride, const int32_t* bp, size_t bp_stride,
+// ---- grid-parallel bulk kernels: ONE THREAD PER BEAD, blockIdx.y = replica.  Any system size and replica count
+// (a 10^6-bead box is one replica spread over the whole GPU; 2368 small replicas are 2368 rows of CTAs).
+// They read the tables through global memory (L1/L2 resident) instead of staging 31 KB per small CTA.
+constexpr int BULK_THREADS = 256;
+__device__ __forceinline__ bool bulk_bind(Rep& r, const DevArrays& d, int r0, int& k) {
+  rep_bind(r, d, staged_global(d), nullptr, r0 + blockIdx.y);
+  k = blockIdx.x * BULK_THREADS + threadIdx.x;
+  return k < r.N;
+}
+__device__ __forceinline__ void bulk_error(Rep& r, int code, int info) {  // first error of the replica wins
+  if (atomicCAS(&r.sc->error, 0, code) == 0) r.sc->error_info = info;
+}
+
+// clears the error word and the fix-up hit counter of each replica before a run start
+__global__ void dmd_bulk_reset_kernel(DevArrays d, int r0, int nrep) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nrep) return;
+  RepScalars& q = d.scal[r0 + k];
+  q.error = 0;
+  q.error_info = 0;
+  q.pad[0] = 0;
+}
+
+// run start, step 1 (inputinfo.f:89-91, main.F90:143-156, 205-234, 408-423): records, scalars, calendar
+__global__ void __launch_bounds__(BULK_THREADS) dmd_bulk_init_kernel(DevArrays d, int r0, const double* sv, size_t sv_stride,
+                                                                      const int32_t* bp, size_t bp_stride,
                                                                       const double* tstar, unsigned long long seed0) {
-  __shared__ SmemConsts sconst;
-  const Staged tab = stage_consts(d, &sconst);
+  Rep r;
+  int k;
+  bulk_bind(r, d, r0, k);
+  const int rid = r0 + blockIdx.y;
+  const size_t c = blockIdx.y;
+  init_scalars(r, tstar[rid], seed0 + (unsigned long long)rid);  // identical in every thread; lane 0 of each warp
+                                                                 // stores the same tallies
+  const double tghost = first_ghost_time(r);
+  if (k < r.N && !init_bead(r, k, sv + c * sv_stride, bp ? bp + c * bp_stride : nullptr)) bulk_error(r, DMD_E_BAD_INPUT, k);
+  if (k < d.cal_stride) r.cal[k] = init_cal_entry(r, k, tghost);
+  if (k == 0) {  // the one copy of the scalars that is stored
+    RepScalars& q = *r.sc;
+    q.t = r.t; q.tfalse = r.tfalse; q.old_tfalse = r.old_tfalse; q.setemp = r.setemp; q.interval = r.interval;
+    q.t_fact = r.t_fact; q.interval_max = r.interval_max; q.n_forced = r.n_forced; q.avegtime = r.avegtime;
+    q.coll = r.coll; q.rng_ctr = r.ctr; q.n_pair_pred = 0; q.n_nbr_visits = 0;
+    q.n_log = 0; q.n_out = 0;
+  }
+}
+
+// cell_add.f:12-28
+__global__ void __launch_bounds__(BULK_THREADS) dmd_bulk_cell_kernel(DevArrays d, int r0) {
+  Rep r;
+  int k;
+  if (!bulk_bind(r, d, r0, k)) return;
+  cell_build(r, k, 1 << 30);
+}
+__global__ void __launch_bounds__(BULK_THREADS) dmd_bulk_clear_kernel(DevArrays d, int r0) {
+  Rep r;
+  int k;
+  if (!bulk_bind(r, d, r0, k)) return;
+  cell_clear(r, k, 1 << 30);
+}
+
+// run start, step 2 (main.F90:249-321): every N / C bead looks through its cell stencil for the pairs the literal
+// double loop acts on (the N-C well, 4.5 A, is shorter than the stencil reach) and appends them to scratch
+__global__ void __launch_bounds__(BULK_THREADS) dmd_bulk_hits_kernel(DevArrays d, int r0) {
+  Rep r;
+  int k;
+  if (!bulk_bind(r, d, r0, k)) return;
+  const uint32_t mk = r.c.meta[k];
+  const int cls = meta_cls(mk);
+  if ((cls != 1 && cls != 2) || r.cnext[k] == -2) return;
+  const SysConst& s = *r.c.sys;
+  const BeadRec a = r.rec[k];
+  const int ck = r.c.chain[k];
+  int32_t* hits = reinterpret_cast<int32_t*>(r.up);
+  const int hit_cap = (int)(((size_t)r.N * r.cap) / 4);
+  int32_t* counter = &r.sc->pad[0];
+  auto emit = [&](int kj) {
+    const int pos = atomicAdd(counter, 1);
+    if (pos < hit_cap) {
+      hits[2 * pos] = k;
+      hits[2 * pos + 1] = kj;
+    }
+  };
+  if (a.bptnr > k) emit(a.bptnr);  // bonded pairs act whatever their distance
+  int cx, cy, cz;
+  cell_coords(s, a, cx, cy, cz);
+  const int ncr = s.ncr;
+  for (int dz = -2; dz <= 2; dz++) {
+    int z = cz + dz;
+    z = z < 0 ? z + ncr : (z >= ncr ? z - ncr : z);
+    for (int dy = -2; dy <= 2; dy++) {
+      int y = cy + dy;
+      y = y < 0 ? y + ncr : (y >= ncr ? y - ncr : y);
+      for (int dx = -2; dx <= 2; dx++) {
+        int x = cx + dx;
+        x = x < 0 ? x + ncr : (x >= ncr ? x - ncr : x);
+        for (int kj = r.cellhead[(y + z * ncr) * ncr + x]; kj >= 0; kj = r.cnext[kj]) {
+          if (kj <= k || kj == a.bptnr) continue;
+          const int cj = meta_cls(r.c.meta[kj]);
+          if (cj != 1 && cj != 2) continue;
+          if (fixup_pair_hit(r, k, a, mk, ck, kj)) emit(kj);
+        }
+      }
+    }
+  }
+}
+// ... and one warp per replica replays them in the loop's order
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_fixup_kernel(DevArrays d, int r0, int nrep) {
   int rid = replica_of_warp(r0, nrep);
   if (rid < 0) return;
   Rep r;
-  rep_bind(r, d, tab, warp_queue(), rid);
-  const size_t k = (size_t)(rid - r0);
-  init_replica(r, sv + k * sv_stride, bp ? bp + k * bp_stride : nullptr, tstar[rid], seed0 + (unsigned long long)rid,
-               d.nc_beads, d.n_nc, d.cal_stride);
-  rep_save(r);
+  rep_bind(r, d, staged_global(d), nullptr, rid);
+  int32_t* hits = reinterpret_cast<int32_t*>(r.up);
+  const int hit_cap = (int)(((size_t)r.N * r.cap) / 4);
+  int nh = r.sc->pad[0];
+  if (nh > hit_cap) {
+    if (Warp::lane() == 0) bulk_error(r, DMD_E_NBR_CAP, nh);
+    nh = 0;
+  }
+  fixup_replay(r, hits, nh, hit_cap);
+}
+
+// nbor.f:33-137
+__global__ void __launch_bounds__(BULK_THREADS) dmd_bulk_nbor_kernel(DevArrays d, int r0) {
+  Rep r;
+  int k;
+  const bool in = bulk_bind(r, d, r0, k);
+  r.error = 0;
+  nbor_build<false>(r, in ? k : r.N, 1 << 30);  // every thread takes part in the warp votes inside
+  if (r.error && Warp::lane() == 0) bulk_error(r, r.error, r.error_info);
+}
+
+// events.f:23-107
+__global__ void __launch_bounds__(BULK_THREADS) dmd_bulk_predict_kernel(DevArrays d, int r0) {
+  Rep r;
+  int k;
+  if (!bulk_bind(r, d, r0, k)) return;
+  redo_lane(r, k);
+}
+// per-group calendar minima of the warp-per-replica engine: one warp per group of 32 entries
+__global__ void __launch_bounds__(BULK_THREADS) dmd_bulk_groups_kernel(DevArrays d, int r0) {
+  Rep r;
+  rep_bind(r, d, staged_global(d), nullptr, r0 + blockIdx.y);
+  const int g = blockIdx.x * (BULK_THREADS / 32) + (threadIdx.x >> 5);
+  if (g < r.G) group_min_update(r, g);
 }
 
 // device state -> the reference's sv(6,N) and bptnr(N) (1-based), for dmdb_get_state_all
@@ -392,11 +483,31 @@ inline bool block_engine_fits(const dmd::SysConst& s) {
   return dmd::blk_layout(s.N, s.ngroups * 32, smem_optin()).total <= smem_optin();
 }
 
+inline dim3 bulk_grid(const dmd::DevArrays& d, int nrep, int n) { return dim3((n + dmd::BULK_THREADS - 1) / dmd::BULK_THREADS, nrep); }
+inline void launch_nbor(const dmd::DevArrays& d, int r0, int nrep) {  // = nbor(): cell_add.f + nbor.f
+  using namespace dmd;
+  const dim3 g = bulk_grid(d, nrep, d.n_beads);
+  dmd_bulk_cell_kernel<<<g, BULK_THREADS, 0, g_stream>>>(d, r0);
+  dmd_bulk_nbor_kernel<<<g, BULK_THREADS, 0, g_stream>>>(d, r0);
+  dmd_bulk_clear_kernel<<<g, BULK_THREADS, 0, g_stream>>>(d, r0);
+}
+inline void launch_predict_all(const dmd::DevArrays& d, int r0, int nrep) {  // = events()
+  using namespace dmd;
+  dmd_bulk_predict_kernel<<<bulk_grid(d, nrep, d.n_beads), BULK_THREADS, 0, g_stream>>>(d, r0);
+  const int groups = d.cal_stride / 32;
+  dmd_bulk_groups_kernel<<<dim3((groups + BULK_THREADS / 32 - 1) / (BULK_THREADS / 32), nrep), BULK_THREADS, 0, g_stream>>>(d, r0);
+}
 inline void run_init(const dmd::DevArrays& d, int r0, int nrep, const double* sv, size_t sv_stride, const int32_t* bp,
                      size_t bp_stride, const double* tstar, unsigned long long seed0) {
   using namespace dmd;
-  const int grid = (nrep + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-  dmd_init_kernel<<<grid, WARPS_PER_CTA * 32, 0, g_stream>>>(d, r0, nrep, sv, sv_stride, bp, bp_stride, tstar, seed0);
+  const int n = d.cal_stride > d.n_beads ? d.cal_stride : d.n_beads;
+  dmd_bulk_reset_kernel<<<(nrep + 255) / 256, 256, 0, g_stream>>>(d, r0, nrep);
+  dmd_bulk_init_kernel<<<bulk_grid(d, nrep, n), BULK_THREADS, 0, g_stream>>>(d, r0, sv, sv_stride, bp, bp_stride, tstar, seed0);
+  const dim3 g = bulk_grid(d, nrep, d.n_beads);
+  dmd_bulk_cell_kernel<<<g, BULK_THREADS, 0, g_stream>>>(d, r0);
+  dmd_bulk_hits_kernel<<<g, BULK_THREADS, 0, g_stream>>>(d, r0);
+  dmd_bulk_clear_kernel<<<g, BULK_THREADS, 0, g_stream>>>(d, r0);
+  dmd_fixup_kernel<<<(nrep + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, 0, g_stream>>>(d, r0, nrep);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(g_stream));
 }
@@ -411,11 +522,12 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
   using namespace dmd;
   const int block = WARPS_PER_CTA * 32;
   const int grid = (nrep + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  int nl = 1;
   CUDA_OK(cudaEventRecord(g_ev0, g_stream));
   switch (op) {
-    case 0: dmd_start_kernel<<<grid, block, 0, g_stream>>>(d, r0, nrep); break;
-    case 1: dmd_nbor_kernel<<<grid, block, 0, g_stream>>>(d, r0, nrep); break;
-    case 2: dmd_predict_all_kernel<<<grid, block, 0, g_stream>>>(d, r0, nrep); break;
+    case 0: launch_nbor(d, r0, nrep); launch_predict_all(d, r0, nrep); nl = 5; break;
+    case 1: launch_nbor(d, r0, nrep); nl = 3; break;
+    case 2: launch_predict_all(d, r0, nrep); nl = 2; break;
     case 3: dmd_event_loop_kernel<<<grid, block, 0, g_stream>>>(d, r0, nrep, arg); break;
     case 4: dmd_sync_positions_kernel<<<grid, block, 0, g_stream>>>(d, r0, nrep); break;
     case 5: dmd_energy_kernel<<<grid, block, 0, g_stream>>>(d, r0, nrep, eout); break;
@@ -440,7 +552,7 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
   float t = 0;
   CUDA_OK(cudaEventElapsedTime(&t, g_ev0, g_ev1));
   if (ms) *ms = t;
-  if (launches) *launches = 1;
+  if (launches) *launches = nl;
 }
 
 }  // namespace be

@@ -1264,100 +1264,48 @@ DMD_DEV void sync_positions(Rep& r) {
 // loop can act on -- N-C pairs inside their well with ev_code 15 and non-terminal beads, and bonded pairs -- into
 // scratch (the not yet built up-list array), then they are ranked lexicographically and lane 0 replays them.
 // ---------------------------------------------------------------------------------------------------------
-DMD_DEV void init_replica(Rep& r, const double* sv, const int32_t* bptnr1, double tstar, uint64_t seed,
-                          const int32_t* nc, int n_nc, int cal_stride) {
+// per-bead part of the run start: wrap, record, er34, oldr; returns false on a bad bptnr entry
+DMD_DEV bool init_bead(Rep& r, int k, const double* sv, const int32_t* bptnr1) {
+  BeadRec b;
+  double x = sv[6 * (size_t)k], y = sv[6 * (size_t)k + 1], z = sv[6 * (size_t)k + 2];
+  x = x - dmd_round(x); y = y - dmd_round(y); z = z - dmd_round(z);  // inputinfo.f:89-91
+  x = x - dmd_round(x); y = y - dmd_round(y); z = z - dmd_round(z);  // main.F90:206-208
+  b.x = x; b.y = y; b.z = z;
+  b.vx = sv[6 * (size_t)k + 3]; b.vy = sv[6 * (size_t)k + 4]; b.vz = sv[6 * (size_t)k + 5];
+  int bp = bptnr1 ? bptnr1[k] - 1 : -1;
+  const bool ok = bp >= -1 && bp < r.N;
+  b.bptnr = ok ? bp : -1;
+  b.er1 = b.er2 = -1;
+  b.ident = (uint8_t)meta_id0(r.c.meta[k]);
+  b.ov1 = b.ov2 = 1;
+  b.pad = 0;
+  r.rec[k] = b;
+  r.er34[2 * k] = -1;
+  r.er34[2 * k + 1] = -1;
+  r.oldr[3 * k] = x; r.oldr[3 * k + 1] = y; r.oldr[3 * k + 2] = z;
+  return ok;
+}
+
+// does the literal k < k_j loop of main.F90:249-321 act on the pair (k, kj)?  Either the geometric test of
+// :262-283 (N-C pair with identities 1 + 4 inside its well, ev_code 15, both beads non-terminal) or a bonded pair
+DMD_DEV bool fixup_pair_hit(const Rep& r, int k, const BeadRec& a, uint32_t mk, int ck, int kj) {
+  if (kj == a.bptnr) return true;
+  const BeadRec b = r.rec[kj];
+  if (a.ident + b.ident != 5) return false;
   const SysConst& s = *r.c.sys;
-  const int N = r.N;
-  r.error = 0;
-  r.error_info = 0;
+  double rx = a.x - b.x, ry = a.y - b.y, rz = a.z - b.z;
+  rx = rx - dmd_round(rx); ry = ry - dmd_round(ry); rz = rz - dmd_round(rz);
+  const double rijsq = rx * rx + ry * ry + rz * rz;
+  const double diff = rijsq - r.c.tab->welldia_sq[tix(a.ident, b.ident)];
+  const uint32_t mj = r.c.meta[kj];
+  return diff < 0.0 && static_code(s, mk, ck, k, mj, r.c.chain[kj], kj) == 15 && !is_terminal_bead(s, mk) &&
+         !is_terminal_bead(s, mj);
+}
+
+// the fix-up is order dependent (identity changes made on the way affect later tests, and a later repuls_add
+// overwrites an earlier one): rank the collected pairs lexicographically, then lane 0 replays the loop body
+DMD_DEV void fixup_replay(Rep& r, int32_t* hits, int nh, int hit_cap) {
   Warp::sync();
-  for (int k = Warp::lane(); k < N; k += DMD_W) {
-    BeadRec b;
-    double x = sv[6 * (size_t)k], y = sv[6 * (size_t)k + 1], z = sv[6 * (size_t)k + 2];
-    x = x - dmd_round(x); y = y - dmd_round(y); z = z - dmd_round(z);  // inputinfo.f:89-91
-    x = x - dmd_round(x); y = y - dmd_round(y); z = z - dmd_round(z);  // main.F90:206-208
-    b.x = x; b.y = y; b.z = z;
-    b.vx = sv[6 * (size_t)k + 3]; b.vy = sv[6 * (size_t)k + 4]; b.vz = sv[6 * (size_t)k + 5];
-    int bp = bptnr1 ? bptnr1[k] - 1 : -1;
-    if (bp < -1 || bp >= N) {
-      bp = -1;
-      r.error = DMD_E_BAD_INPUT;  // reported by the host after the launch
-      r.error_info = k;
-    }
-    b.bptnr = bp;
-    b.er1 = b.er2 = -1;
-    b.ident = (uint8_t)meta_id0(r.c.meta[k]);
-    b.ov1 = b.ov2 = 1;
-    b.pad = 0;
-    r.rec[k] = b;
-    r.er34[2 * k] = -1;
-    r.er34[2 * k + 1] = -1;
-    r.oldr[3 * k] = x; r.oldr[3 * k + 1] = y; r.oldr[3 * k + 2] = z;
-  }
-  {  // an input error seen by any lane
-    const unsigned m = Warp::ballot(r.error != 0);
-    if (m) {
-      const int src = dmd_ffs(m) - 1;
-      r.error = Warp::shfl(r.error, src);
-      r.error_info = Warp::shfl(r.error_info, src);
-    }
-  }
-  Warp::sync();
-  // ---- main.F90:249-321, step 1: collect candidate pairs (k < kj) as pairs of ints in scratch
-  int32_t* hits = reinterpret_cast<int32_t*>(r.up);
-  const int hit_cap = (int)(((size_t)N * r.cap) / 4);  // first half: unsorted, second half: sorted
-  int nh = 0;
-  for (int base = 0; base < n_nc; base += DMD_W) {
-    const int ik = base + Warp::lane();
-    const int k = ik < n_nc ? nc[ik] : -1;
-    BeadRec a;
-    uint32_t mk = 0;
-    int ck = 0;
-    if (k >= 0) {
-      a = r.rec[k];
-      mk = r.c.meta[k];
-      ck = r.c.chain[k];
-    }
-    int ij = ik + 1;
-    while (true) {
-      // next pair of this lane that qualifies
-      bool found = false;
-      int kj = -1;
-      while (k >= 0 && ij < n_nc) {
-        kj = nc[ij];
-        ij++;
-        const BeadRec b = r.rec[kj];
-        bool hit = kj == a.bptnr;
-        if (!hit && a.ident + b.ident == 5) {
-          double rx = a.x - b.x, ry = a.y - b.y, rz = a.z - b.z;
-          rx = rx - dmd_round(rx); ry = ry - dmd_round(ry); rz = rz - dmd_round(rz);
-          const double rijsq = rx * rx + ry * ry + rz * rz;
-          const double diff = rijsq - r.c.tab->welldia_sq[tix(a.ident, b.ident)];
-          const uint32_t mj = r.c.meta[kj];
-          hit = diff < 0.0 && static_code(s, mk, ck, k, mj, r.c.chain[kj], kj) == 15 && !is_terminal_bead(s, mk) &&
-                !is_terminal_bead(s, mj);
-        }
-        if (hit) {
-          found = true;
-          break;
-        }
-      }
-      const unsigned m = Warp::ballot(found);
-      if (!m) break;
-      const int pos = nh + dmd_popc(m & ((1u << Warp::lane()) - 1u));
-      if (found && pos < hit_cap) {
-        hits[2 * pos] = k;
-        hits[2 * pos + 1] = kj;
-      }
-      nh += dmd_popc(m);
-    }
-  }
-  if (nh > hit_cap) {
-    set_error(r, DMD_E_NBR_CAP, nh);
-    nh = 0;
-  }
-  Warp::sync();
-  // ---- step 2: lexicographic rank of every pair, then lane 0 replays them in the literal loop order
   int32_t* sorted = hits + 2 * (size_t)hit_cap;
   for (int h = Warp::lane(); h < nh; h += DMD_W) {
     const int k = hits[2 * h], kj = hits[2 * h + 1];
@@ -1371,6 +1319,7 @@ DMD_DEV void init_replica(Rep& r, const double* sv, const int32_t* bptnr1, doubl
   }
   Warp::sync();
   if (Warp::lane() == 0) {
+    const SysConst& s = *r.c.sys;
     for (int h = 0; h < nh; h++) {
       const int k = sorted[2 * h], kj = sorted[2 * h + 1];
       BeadRec* a = &r.rec[k];
@@ -1394,7 +1343,10 @@ DMD_DEV void init_replica(Rep& r, const double* sv, const int32_t* bptnr1, doubl
     }
   }
   Warp::sync();
-  // ---- time constants and tallies (main.F90:127, 143-156), calendar reset (:212-234, 408-423)
+}
+
+// time constants and tallies (main.F90:127, 143-156) in the view's registers + the stored tallies
+DMD_DEV void init_scalars(Rep& r, double tstar, uint64_t seed) {
   r.t = 0.0; r.tfalse = 0.0; r.old_tfalse = 0.0;
   r.setemp = tstar * 12.0;
   r.t_fact = 0.00005;
@@ -1413,17 +1365,91 @@ DMD_DEV void init_replica(Rep& r, const double* sv, const int32_t* bptnr1, doubl
     q.numghosts = q.nupdates = q.nforcedupdate = 0;
     q.rng_seed = seed;
   }
-  for (int k = Warp::lane(); k < cal_stride; k += DMD_W) {
-    CalEnt e;
-    e.t = T_PAD; e.ptnr = -1; e.type = -1;
-    if (k < N) e.t = r.interval_max + 1e-10;  // main.F90:212
-    else if (k < N + 3) {
-      e.t = k == N ? 1000000000.0 : (k == N + 1 ? r.interval : 3.3 / (dmd_sqrt(r.setemp)) + 5);  // :416,421,423
-      e.ptnr = -2;
-      e.type = -2;
-    }
-    r.cal[k] = e;
+}
+
+// calendar entry k at run start: main.F90:212-234, 408-423; the first ghost time is drawn here (:408-416)
+DMD_DEV CalEnt init_cal_entry(const Rep& r, int k, double tghost) {
+  CalEnt e;
+  e.t = T_PAD; e.ptnr = -1; e.type = -1;
+  if (k < r.N) e.t = r.interval_max + 1e-10;
+  else if (k < r.N + 3) {
+    e.t = k == r.N ? tghost : (k == r.N + 1 ? r.interval : 3.3 / (dmd_sqrt(r.setemp)) + 5);
+    e.ptnr = -2;
+    e.type = -2;
   }
+  return e;
+}
+DMD_DEV double first_ghost_time(Rep& r) {  // main.F90:408-416 (advances the replica's RNG counter)
+  if (!r.c.sys->canon) return 1000000000.0;
+  double tgho = 0.0;
+  while (tgho < 1e-18 || tgho == 1.0) tgho = rng_uniform(r.seed, r.ctr);
+  return -1.0 * dmd_log(tgho) * r.avegtime * .0000001;
+}
+
+// the whole run start by ONE warp (host trace build; the CUDA backend spreads the same steps over the grid)
+DMD_DEV void init_replica(Rep& r, const double* sv, const int32_t* bptnr1, double tstar, uint64_t seed,
+                          const int32_t* nc, int n_nc, int cal_stride) {
+  const int N = r.N;
+  r.error = 0;
+  r.error_info = 0;
+  Warp::sync();
+  int bad = -1;
+  for (int k = Warp::lane(); k < N; k += DMD_W)
+    if (!init_bead(r, k, sv, bptnr1)) bad = k;
+  {
+    const unsigned m = Warp::ballot(bad >= 0);
+    if (m) {
+      r.error = DMD_E_BAD_INPUT;  // reported by the host after the launch
+      r.error_info = Warp::shfl(bad, dmd_ffs(m) - 1);
+    }
+  }
+  Warp::sync();
+  // ---- main.F90:249-321, step 1: collect the pairs (k < kj) the loop acts on into scratch (the not yet built
+  // up-list array: first half unsorted, second half sorted)
+  int32_t* hits = reinterpret_cast<int32_t*>(r.up);
+  const int hit_cap = (int)(((size_t)N * r.cap) / 4);
+  int nh = 0;
+  for (int base = 0; base < n_nc; base += DMD_W) {
+    const int ik = base + Warp::lane();
+    const int k = ik < n_nc ? nc[ik] : -1;
+    BeadRec a;
+    uint32_t mk = 0;
+    int ck = 0;
+    if (k >= 0) {
+      a = r.rec[k];
+      mk = r.c.meta[k];
+      ck = r.c.chain[k];
+    }
+    int ij = ik + 1;
+    while (true) {
+      bool found = false;  // next pair of this lane that qualifies
+      int kj = -1;
+      while (k >= 0 && ij < n_nc) {
+        kj = nc[ij];
+        ij++;
+        if (fixup_pair_hit(r, k, a, mk, ck, kj)) {
+          found = true;
+          break;
+        }
+      }
+      const unsigned m = Warp::ballot(found);
+      if (!m) break;
+      const int pos = nh + dmd_popc(m & ((1u << Warp::lane()) - 1u));
+      if (found && pos < hit_cap) {
+        hits[2 * pos] = k;
+        hits[2 * pos + 1] = kj;
+      }
+      nh += dmd_popc(m);
+    }
+  }
+  if (nh > hit_cap) {
+    set_error(r, DMD_E_NBR_CAP, nh);
+    nh = 0;
+  }
+  fixup_replay(r, hits, nh, hit_cap);
+  init_scalars(r, tstar, seed);
+  const double tghost = first_ghost_time(r);
+  for (int k = Warp::lane(); k < cal_stride; k += DMD_W) r.cal[k] = init_cal_entry(r, k, tghost);
   Warp::sync();
 }
 

@@ -134,11 +134,6 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
       rep_bind(r, d, staged_global(d), cq, rid);
       switch (op) {
         case 0:
-          if (d.sys->canon) {
-            double tgho = 0.0;
-            while (tgho < 1e-18 || tgho == 1.0) tgho = rng_uniform(r.seed, r.ctr);
-            r.cal[r.N].t = -1.0 * dmd_log(tgho) * r.avegtime * .0000001;
-          }
           nbor(r);
           predict_all(r);
           rep_save(r);
