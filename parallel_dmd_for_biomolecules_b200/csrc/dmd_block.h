@@ -396,7 +396,7 @@ __device__ __noinline__ void blk_interval_event(BlkShared& S, Rep& r, int w, int
     __syncthreads();
     cell_build(r, tid, nt);
     __syncthreads();
-    nbor_build<true>(r, tid, nt);
+    nbor_build(r, tid, nt);
     __syncthreads();
     cell_clear(r, tid, nt);
     for (int l = tid; l < N; l += nt) redo_lane(r, l);  // events(): every bead from interval_max + ltstep

@@ -157,9 +157,10 @@ int dmdb_create(const dmdb_params* p, const dmdb_topology* topo, const dmdb_tabl
     d.nup = dalloc<uint16_t>(h.get(), R * N);
     d.ndn = dalloc<uint16_t>(h.get(), R * N);
     d.oldr = dalloc<double>(h.get(), R * 3 * N);
-    const size_t nc3 = (size_t)s.ncr * s.ncr * s.ncr;
+    const size_t ncc = (size_t)((s.ncr + 1) >> 1), nc3 = ncc * ncc * ncc;
     d.cellhead = dalloc<int32_t>(h.get(), R * nc3);
     be::fill_i32(d.cellhead, -1, R * nc3);
+    d.cpk = dalloc<uint32_t>(h.get(), R * N);
     d.cnext = dalloc<int32_t>(h.get(), R * N);
     d.cellof = dalloc<int32_t>(h.get(), R * N);
     d.tmin1 = dalloc<double>(h.get(), R * s.ngroups);

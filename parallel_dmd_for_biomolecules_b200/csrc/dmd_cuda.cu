@@ -320,7 +320,6 @@ __global__ void __launch_bounds__(BULK_THREADS) dmd_bulk_hits_kernel(DevArrays d
   const uint32_t mk = r.c.meta[k];
   const int cls = meta_cls(mk);
   if ((cls != 1 && cls != 2) || r.cnext[k] == -2) return;
-  const SysConst& s = *r.c.sys;
   const BeadRec a = r.rec[k];
   const int ck = r.c.chain[k];
   int32_t* hits = reinterpret_cast<int32_t*>(r.up);
@@ -334,27 +333,12 @@ __global__ void __launch_bounds__(BULK_THREADS) dmd_bulk_hits_kernel(DevArrays d
     }
   };
   if (a.bptnr > k) emit(a.bptnr);  // bonded pairs act whatever their distance
-  int cx, cy, cz;
-  cell_coords(s, a, cx, cy, cz);
-  const int ncr = s.ncr;
-  for (int dz = -2; dz <= 2; dz++) {
-    int z = cz + dz;
-    z = z < 0 ? z + ncr : (z >= ncr ? z - ncr : z);
-    for (int dy = -2; dy <= 2; dy++) {
-      int y = cy + dy;
-      y = y < 0 ? y + ncr : (y >= ncr ? y - ncr : y);
-      for (int dx = -2; dx <= 2; dx++) {
-        int x = cx + dx;
-        x = x < 0 ? x + ncr : (x >= ncr ? x - ncr : x);
-        for (int kj = r.cellhead[(y + z * ncr) * ncr + x]; kj >= 0; kj = r.cnext[kj]) {
-          if (kj <= k || kj == a.bptnr) continue;
-          const int cj = meta_cls(r.c.meta[kj]);
-          if (cj != 1 && cj != 2) continue;
-          if (fixup_pair_hit(r, k, a, mk, ck, kj)) emit(kj);
-        }
-      }
-    }
-  }
+  stencil_visit(r, k, [&](int kj) {
+    if (kj <= k || kj == a.bptnr) return;
+    const int cj = meta_cls(r.c.meta[kj]);
+    if (cj != 1 && cj != 2) return;
+    if (fixup_pair_hit(r, k, a, mk, ck, kj)) emit(kj);
+  });
 }
 // ... and one warp per replica replays them in the loop's order
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_fixup_kernel(DevArrays d, int r0, int nrep) {
@@ -378,7 +362,7 @@ __global__ void __launch_bounds__(BULK_THREADS) dmd_bulk_nbor_kernel(DevArrays d
   int k;
   const bool in = bulk_bind(r, d, r0, k);
   r.error = 0;
-  nbor_build<false>(r, in ? k : r.N, 1 << 30);  // every thread takes part in the warp votes inside
+  nbor_build(r, in ? k : r.N, 1 << 30);  // every thread takes part in the warp votes inside
   if (r.error && Warp::lane() == 0) bulk_error(r, r.error, r.error_info);
 }
 

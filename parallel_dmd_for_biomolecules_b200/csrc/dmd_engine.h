@@ -37,6 +37,7 @@ struct Rep {
   uint16_t *nup, *ndn;
   double* oldr;
   int32_t *cellhead, *cnext, *cellof;
+  uint32_t* cpk;  // packed fine cell coordinates of each bead (10 bits per dimension)
   double* tmin1;
   RepScalars* sc;
   EventLogRec* log;
@@ -94,8 +95,9 @@ DMD_DEV void rep_bind(Rep& r, const DevArrays& d, const Staged& st, int32_t* cq,
   r.nup = d.nup + rr * N;
   r.ndn = d.ndn + rr * N;
   r.oldr = d.oldr + rr * 3 * N;
-  const size_t nc3 = (size_t)s->ncr * s->ncr * s->ncr;
+  const size_t ncc = (size_t)((s->ncr + 1) >> 1), nc3 = ncc * ncc * ncc;
   r.cellhead = d.cellhead + rr * nc3;
+  r.cpk = d.cpk + rr * N;
   r.cnext = d.cnext + rr * N;
   r.cellof = d.cellof + rr * N;
   r.tmin1 = d.tmin1 + rr * s->ngroups;
@@ -856,11 +858,76 @@ DMD_DEV int exch(int32_t* p, int v) {
 #endif
 }
 
+// The reference bins beads into cells of width rl/2 and searches the 5 x 5 x 5 block around a bead's cell
+// (n_wrap = 2, cell_link.f:16-94).  At the shipped concentrations that grid is almost empty (0.02 beads per
+// cell), so 125 list heads are probed to find ~15 candidates.  Here the linked lists hang off a COARSE grid of
+// 2 x 2 x 2 fine cells (at most 4 distinct coarse cells per dimension cover the fine range c-2..c+2, 27 in the
+// typical case), and a candidate is kept iff its FINE cell -- computed with the reference's own fp64 division,
+// cell_add.f:22 -- lies in the reference's 5 x 5 x 5 block.  The neighbour SETS are therefore the reference's.
+DMD_DEV uint32_t cpk_pack(int cx, int cy, int cz) { return (uint32_t)cx | ((uint32_t)cy << 10) | ((uint32_t)cz << 20); }
+DMD_DEV int coarse_dim(int ncr) { return (ncr + 1) >> 1; }
+
+// the distinct coarse indices of the fine cells c-2 .. c+2 (periodic) -> out[0..n)
+DMD_DEV int coarse_span(int c, int ncr, int* out) {
+  int n = 0;
+#pragma unroll
+  for (int d = -2; d <= 2; d++) {
+    int f = c + d;
+    f = f < 0 ? f + ncr : (f >= ncr ? f - ncr : f);
+    const int cc = f >> 1;
+    // consecutive fine cells: a repeat is either the previous value or (after wrapping round a small ring) the first
+    if (n == 0 || (out[n - 1] != cc && out[0] != cc)) out[n++] = cc;
+  }
+  return n;
+}
+
+DMD_DEV bool in_fine_stencil(uint32_t pk, uint32_t pj, int ncr) {
+  int dx = (int)(pk & 1023u) - (int)(pj & 1023u), dy = (int)((pk >> 10) & 1023u) - (int)((pj >> 10) & 1023u),
+      dz = (int)(pk >> 20) - (int)(pj >> 20);
+  dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy; dz = dz < 0 ? -dz : dz;
+  dx = dx > ncr - dx ? ncr - dx : dx; dy = dy > ncr - dy ? ncr - dy : dy; dz = dz > ncr - dz ? ncr - dz : dz;
+  return dx <= 2 && dy <= 2 && dz <= 2;
+}
+
+// f(j) for every bead j != k whose cell lies in the 5 x 5 x 5 block around the cell of bead k
+template <class F>
+DMD_DEV void stencil_visit(const Rep& r, int k, F f) {
+  const int ncr = r.c.sys->ncr, ncc = coarse_dim(ncr);
+  const uint32_t pk = r.cpk[k];
+  int xs[4], ys[4], zs[4];
+  const int nx = coarse_span((int)(pk & 1023u), ncr, xs), ny = coarse_span((int)((pk >> 10) & 1023u), ncr, ys),
+            nz = coarse_span((int)(pk >> 20), ncr, zs);
+  // ONE visit site, no unrolling: the lanes of a warp walk different cells and chains, and they can only
+  // re-converge on the (expensive) body of f if there is a single copy of it
+  const int nrow = ny * nz;
+#pragma unroll 1
+  for (int row = 0; row < nrow; row++) {
+    const int iz = row / ny, iy = row - iz * ny;
+    const int rowbase = (ys[iy] + zs[iz] * ncc) * ncc;
+    int h0 = r.cellhead[rowbase + xs[0]], h1 = -1, h2 = -1, h3 = -1;  // the row's heads: loads in flight together
+    if (nx > 1) h1 = r.cellhead[rowbase + xs[1]];
+    if (nx > 2) h2 = r.cellhead[rowbase + xs[2]];
+    if (nx > 3) h3 = r.cellhead[rowbase + xs[3]];
+    int ix = 0, j = h0;
+#pragma unroll 1
+    while (true) {
+      if (j < 0) {  // next chain of the row
+        ix++;
+        if (ix >= nx) break;
+        j = ix == 1 ? h1 : (ix == 2 ? h2 : h3);
+        continue;
+      }
+      if (j != k && in_fine_stencil(pk, r.cpk[j], ncr)) f(j);
+      j = r.cnext[j];
+    }
+  }
+}
+
 // (t0, ts): first bead and stride of the calling thread -- (lane, DMD_W) when one warp owns the replica,
-// (thread index, CTA size) when a whole CTA does (dmd_block.h)
+// (thread index, CTA size) when a whole CTA does (dmd_block.h), (global thread, "infinite") in the bulk kernels
 DMD_DEV void cell_build(Rep& r, int t0 = Warp::lane(), int ts = DMD_W) {
   const SysConst& s = *r.c.sys;
-  const int ncr = s.ncr, nc = s.num_cell, nw = s.n_wrap;
+  const int ncr = s.ncr, nc = s.num_cell, nw = s.n_wrap, ncc = coarse_dim(ncr);
   Warp::sync();
   for (int k = t0; k < r.N; k += ts) {
     int cx, cy, cz;
@@ -869,102 +936,79 @@ DMD_DEV void cell_build(Rep& r, int t0 = Warp::lane(), int ts = DMD_W) {
     if (cx < 0 || cy < 0 || cz < 0 || cx >= ncr || cy >= ncr || cz >= ncr) {
       // the reference would file the bead in a ghost cell that is never looked up
       r.cnext[k] = -2;
+      r.cpk[k] = 0;
       continue;
     }
-    int cidx = cx + (cy + cz * ncr) * ncr;
+    r.cpk[k] = cpk_pack(cx, cy, cz);
+    const int cidx = (cx >> 1) + ((cy >> 1) + (cz >> 1) * ncc) * ncc;
     r.cnext[k] = exch(&r.cellhead[cidx], k);
   }
   Warp::sync();
 }
 
 DMD_DEV void cell_clear(Rep& r, int t0 = Warp::lane(), int ts = DMD_W) {
-  const SysConst& s = *r.c.sys;
-  const int ncr = s.ncr;
+  const int ncc = coarse_dim(r.c.sys->ncr);
   Warp::sync();
   for (int k = t0; k < r.N; k += ts) {
     if (r.cnext[k] == -2) continue;
-    int cx, cy, cz;
-    cell_coords(s, r.rec[k], cx, cy, cz);
-    r.cellhead[cx + (cy + cz * ncr) * ncr] = -1;
+    const uint32_t pk = r.cpk[k];
+    r.cellhead[(int)((pk & 1023u) >> 1) + ((int)(((pk >> 10) & 1023u) >> 1) + (int)((pk >> 20) >> 1) * ncc) * ncc] = -1;
   }
   Warp::sync();
 }
 
-template <bool PREFETCH>
+// nbor.f:33-137: class rule nbor.f:60 (bonded-class pairs are neighbours whenever found in the stencil) /
+// distance rule nbor.f:97-105; up list (partners > k) and down list (partners < k) of every bead
 DMD_DEV void nbor_build(Rep& r, int t0 = Warp::lane(), int ts = DMD_W) {
   const SysConst& s = *r.c.sys;
-  const int ncr = s.ncr, cap = r.cap;
+  const int cap = r.cap;
   int overflow = 0;
   for (int k = t0; k < r.N; k += ts) {
     const BeadRec rk = r.rec[k];
     const uint32_t mk = r.c.meta[k];
     const int ck = r.c.chain[k];
     int nu = 0, nd = 0;
-    if (r.cnext[k] != -2) {
-      int cx, cy, cz;
-      cell_coords(s, rk, cx, cy, cz);
-      // candidate test + list append for bead j found in the stencil of k
-      auto visit = [&](int j) {
-        if (j == k) return;
-        const int sc = static_code(s, mk, ck, k, r.c.meta[j], r.c.chain[j], j);
-        bool in;
-        if (code_is_bonded_class(sc)) {
-          in = true;  // nbor.f:60
-        } else {
-          const BeadRec rj = r.rec[j];
-          const int code = overlay_code(sc, k, rk, j, rj);
-          double rx = rk.x - rj.x, ry = rk.y - rj.y, rz = rk.z - rj.z;  // nbor.f:97-103
-          rx = rx - dmd_round(rx);
-          ry = ry - dmd_round(ry);
-          rz = rz - dmd_round(rz);
-          double rijsq = rx * rx + ry * ry + rz * rz;
-          in = rijsq <= s.rlsq[code];  // nbor.f:105
-        }
-        if (in) {
-          uint32_t e = ((uint32_t)sc << NB_SHIFT) | (uint32_t)j;
-          if (j > k) {
-            if (nu < cap) r.up[(size_t)k * cap + nu] = e;
-            nu++;
-          } else {
-            if (nd < cap) r.dn[(size_t)k * cap + nd] = e;
-            nd++;
-          }
-        }
-      };
-      if (PREFETCH) {
-        // latency-bound caller (one CTA per replica): the 25 heads of a z-plane are loaded together, then walked
-        int xs[5], ys[5];
-#pragma unroll
-        for (int q = 0; q < 5; q++) {
-          int x = cx + q - 2, y = cy + q - 2;
-          xs[q] = x < 0 ? x + ncr : (x >= ncr ? x - ncr : x);
-          ys[q] = y < 0 ? y + ncr : (y >= ncr ? y - ncr : y);
-        }
-        for (int dz = -2; dz <= 2; dz++) {
-          int z = cz + dz;
-          z = z < 0 ? z + ncr : (z >= ncr ? z - ncr : z);
-          int heads[25];
-#pragma unroll
-          for (int q = 0; q < 25; q++) heads[q] = r.cellhead[(ys[q / 5] + z * ncr) * ncr + xs[q % 5]];
-#pragma unroll 1
-          for (int q = 0; q < 25; q++)
-            for (int j = heads[q]; j >= 0; j = r.cnext[j]) visit(j);
-        }
+    auto test_and_append = [&](int j) {
+      const int sc = static_code(s, mk, ck, k, r.c.meta[j], r.c.chain[j], j);
+      bool in;
+      if (code_is_bonded_class(sc)) {
+        in = true;  // nbor.f:60
       } else {
-        for (int dz = -2; dz <= 2; dz++) {
-          int z = cz + dz;
-          z = z < 0 ? z + ncr : (z >= ncr ? z - ncr : z);
-          for (int dy = -2; dy <= 2; dy++) {
-            int y = cy + dy;
-            y = y < 0 ? y + ncr : (y >= ncr ? y - ncr : y);
-            const int rowbase = (y + z * ncr) * ncr;
-            for (int dx = -2; dx <= 2; dx++) {
-              int x = cx + dx;
-              x = x < 0 ? x + ncr : (x >= ncr ? x - ncr : x);
-              for (int j = r.cellhead[rowbase + x]; j >= 0; j = r.cnext[j]) visit(j);
-            }
-          }
+        const BeadRec rj = r.rec[j];
+        const int code = overlay_code(sc, k, rk, j, rj);
+        double rx = rk.x - rj.x, ry = rk.y - rj.y, rz = rk.z - rj.z;  // nbor.f:97-103
+        rx = rx - dmd_round(rx);
+        ry = ry - dmd_round(ry);
+        rz = rz - dmd_round(rz);
+        double rijsq = rx * rx + ry * ry + rz * rz;
+        in = rijsq <= s.rlsq[code];  // nbor.f:105
+      }
+      if (in) {
+        uint32_t e = ((uint32_t)sc << NB_SHIFT) | (uint32_t)j;
+        if (j > k) {
+          if (nu < cap) r.up[(size_t)k * cap + nu] = e;
+          nu++;
+        } else {
+          if (nd < cap) r.dn[(size_t)k * cap + nd] = e;
+          nd++;
         }
+      }
+    };
+    if (r.cnext[k] != -2) {
+      // two steps, so that the lanes of a warp run the expensive test in lockstep: (1) walk the cells and park
+      // the candidates in the bead's (still unused) down-list row, (2) test them one after the other.  Writing
+      // entry nd of the row is safe: nd never exceeds the number of candidates already consumed.
+      uint32_t* park = r.dn + (size_t)k * cap;
+      int nc = 0;
+      stencil_visit(r, k, [&](int j) {
+        if (nc < cap) park[nc] = (uint32_t)j;
+        nc++;
+      });
+      if (nc <= cap) {
+#pragma unroll 1
+        for (int t = 0; t < nc; t++) test_and_append((int)park[t]);
+      } else {  // more candidates than a row holds (very dense region): test them on the fly
+        stencil_visit(r, k, test_and_append);
       }
     }
     if (nu > cap || nd > cap) {
@@ -982,7 +1026,7 @@ DMD_DEV void nbor_build(Rep& r, int t0 = Warp::lane(), int ts = DMD_W) {
 
 DMD_DEV void nbor(Rep& r) {  // nbor.f:33-137
   cell_build(r);
-  nbor_build<false>(r);
+  nbor_build(r);
   cell_clear(r);
 }
 

@@ -237,6 +237,7 @@ inline void build_model(const dmdb_params& p, const dmdb_topology& topo, const d
   s.num_cell = (int)(boxl / (sig_max_all * rl_const) * s.n_wrap) + 2 * s.n_wrap;
   s.ncr = s.num_cell - 2 * s.n_wrap;
   if (s.ncr < 5) throw std::runtime_error("box too small: fewer than 5 real cells per dimension");
+  if (s.ncr > 1023) throw std::runtime_error("box too large: more than 1023 cells per dimension");
   s.width = boxl / (double)(s.num_cell - 2 * s.n_wrap);
   s.half = boxl / 2.0;
   // ---- the hot copies (HotConst + per-residue bond windows)

@@ -161,7 +161,8 @@ struct DevArrays {
   uint16_t* nup;          // N
   uint16_t* ndn;          // N
   double* oldr;           // 3N
-  int32_t* cellhead;      // ncr^3
+  int32_t* cellhead;      // ceil(ncr/2)^3: list heads of the coarse grid (2 x 2 x 2 fine cells)
+  uint32_t* cpk;          // N: packed fine cell coordinates (10 bits per dimension)
   int32_t* cnext;         // N
   int32_t* cellof;        // N (reference cell id of cell_add.f:25, for parity read-back)
   double* tmin1;          // ngroups
