@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--replicas", type=int, default=2368, help="replicas per GPU (148 SMs x 16 warps)")
+    ap.add_argument("--replicas", type=int, default=4144, help="replicas per GPU (148 SMs x 28 warps)")
     ap.add_argument("--events", type=int, default=20000, help="calendar events per replica per step")
     ap.add_argument("--ref-events", type=int, default=400000, help="events per host thread per step (--impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

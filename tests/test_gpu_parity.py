@@ -129,11 +129,11 @@ def test_retemp_and_distinct_states(tab, system_b):
 
 
 def test_full_size_properties(tab, system_b):
-    """BASELINE config 2 at bench size: 2368 replicas of the 48-peptide box.  Size-independent properties:
+    """BASELINE config 2 at bench size: 4144 replicas of the 48-peptide box.  Size-independent properties:
     NVE energy is conserved in every replica, every replica's final state passes checkover.f (sampled), identical
     replicas stay bit-identical, and a second run of the same handle state is deterministic."""
     topo, sv, boxl = system_b
-    R = 2368
+    R = 4144
     p = tables.make_params(boxl=boxl, tstar=0.18, canon=False, n_replicas=R)
     dev = DMD(p, topo, tab)
     dev.set_state(sv)
