@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--events", type=int, default=20000, help="calendar events per replica per step")
     ap.add_argument("--ref-events", type=int, default=400000, help="events per host thread per step (--impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (single trajectory, "
+                    "12 288-bead box, bulk kernels on a 10^6-bead box)")
     return ap.parse_args()
 
 
@@ -119,6 +121,54 @@ def cpu_baseline_sample(tab, topo, sv, seconds_target=12.0):
     return {"value": n / sec, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": "%d events of one replica of the workload after 1e5 warm-up events, C++ oracle (g++ -O2 "
                       "-ffp-contract=off), %.1f s" % (n, sec)}
+
+
+def extras(tab, topo_b, sv_b, peak):
+    """Secondary measurements reported beside the headline (rank 0, 1 GPU): the same event loop on ONE trajectory
+    with the CTA-per-replica engine (batched conservative commit), BASELINE config 4 (192 chains x 16 residues,
+    12 288 beads) and the bulk kernels on BASELINE config 5 (~10^6 beads) with their algorithmic HBM traffic
+    (events() moves 64N + 68 P_up + 16N bytes; nbor() 24N + 4N + 8 P_up plus the candidate scan)."""
+    from parallel_dmd_for_biomolecules_b200 import genconfig, tables
+    from parallel_dmd_for_biomolecules_b200.dmd import DMD
+    out = {}
+    for name, eng in (("warp_per_replica", 1), ("cta_per_replica_batched_commit", 2)):
+        d = DMD(tables.make_params(boxl=BOXL, tstar=TSTAR, canon=True, n_replicas=1, engine=eng), topo_b, tab)
+        d.set_state(sv_b)
+        d.run(20000)
+        n = 100000 if eng == 2 else 30000
+        st = d.run(n)
+        out["single_trajectory_config2_" + name] = {"events_per_s": n / (st.device_ms * 1e-3)}
+        if eng == 2:
+            bs = d.batch_stats()
+            out["single_trajectory_config2_" + name]["events_committed_per_round"] = (bs["executed"] - bs["rolled_back"]) / max(bs["rounds"], 1)
+        d.close()
+    topo4, sv4 = genconfig.generate_box(["KLVFFAEKLVFFAEKL"], [192], 200.0, 0.3, tab, seed=3)
+    d = DMD(tables.make_params(boxl=200.0, tstar=0.3, canon=True, n_replicas=1, engine=2), topo4, tab)
+    d.set_state(sv4)
+    d.run(5000)
+    st = d.run(50000)
+    bs = d.batch_stats()
+    out["config4_12288_beads_one_trajectory"] = {"events_per_s": 50000 / (st.device_ms * 1e-3),
+                                                 "events_committed_per_round": (bs["executed"] - bs["rolled_back"]) / max(bs["rounds"], 1)}
+    d.close()
+    nch = 35715
+    boxl = BOXL * (nch / 48.0) ** (1.0 / 3.0)
+    topo5, sv5 = genconfig.generate_box(["KLVFFAE"], [nch], boxl, 0.5, tab, seed=5)
+    N5 = topo5.n_beads
+    d = DMD(tables.make_params(boxl=boxl, tstar=0.5, canon=True, n_replicas=1, engine=1, nbr_capacity=32), topo5, tab)
+    d.set_state(sv5)
+    p_up = int(d.nbors(0)[0][-1])
+    res = {"beads": N5, "up_pairs": p_up}
+    for name, fn, nbytes in (("events", d.events, 64 * N5 + 68 * p_up + 16 * N5), ("nbor", d.nbor, 28 * N5 + 64 * N5 + 2 * 8 * p_up)):
+        ms = []
+        for _ in range(5):
+            fn()
+            ms.append(d.stats().device_ms)
+        t = min(ms[1:])
+        res[name] = {"device_ms": t, "algorithmic_GB_per_s": nbytes / (t * 1e-3) / 1e9, "frac_of_measured_hbm": nbytes / (t * 1e-3) / 1e9 / peak}
+    out["config5_bulk_kernels"] = res
+    d.close()
+    return out
 
 
 def run_reference(args, rank, world):
@@ -284,6 +334,9 @@ def main():
                          "algorithmic_bytes_per_launch": abytes / args.steps,
                          "note": "latency/issue-bound gather workload: see DESIGN.md 'Roofline'"},
         }
+        if world == 1 and not args.no_extras:
+            d.close()
+            out["extras"] = extras(tab, topo, sv, peak)
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_sample(tab, topo, sv)
         print(json.dumps(out))

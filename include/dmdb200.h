@@ -141,6 +141,10 @@ int dmdb_nbor(dmdb_handle* h);
 int dmdb_predict_all(dmdb_handle* h);
 /* = the main loop main.F90:484-1258 with serial semantics: every replica processes n_events calendar events. */
 int dmdb_run(dmdb_handle* h, int64_t n_events, dmdb_stats* stats);
+/* Same, but every replica returns right after it has processed its next output pseudo-event (main.F90:1191-1246;
+ * every 3.3/sqrt(setemp)+5 time units) or after max_events, whichever comes first: the host then writes the .energy
+ * line (dmdb_energy_of) and the .config / .bptnr / .lastvel records (dmdb_get_state) exactly where the reference does. */
+int dmdb_run_until_output(dmdb_handle* h, int64_t max_events, dmdb_stats* stats);
 /* = main.F90:1288-1295: advance false positions to real positions and wrap (end of run). */
 int dmdb_sync_positions(dmdb_handle* h);
 

@@ -72,6 +72,7 @@ struct BlkShared {
   double moved_far[BK_MAXW];
   double window;
   long long coll, target;
+  int stop_at_output, pad2;
   long long st_rounds, st_exec, st_rollback, st_conflict, st_cold;  // statistics of the batching
   long long n_pair_pred, n_nbr_visits;
   int wmin_i[BK_MAXW];
@@ -482,6 +483,7 @@ DMD_DEV void blk_run(BlkShared& S, Rep& r, uint32_t* claim, int w, int nw) {
           S.n_cand = 0;
           S.tlast = -1.0;
           S.st_cold += 1;
+          if (S.stop_at_output && o == r.N + 2) S.target = r.coll;  // the host takes over after the output event
           if (r.error) {
             S.error = r.error;
             S.error_info = r.error_info;

@@ -289,7 +289,11 @@ int dmdb_predict_all(dmdb_handle* h) {
 
 int dmdb_get_replica_stats(dmdb_handle* h, int replica, dmdb_stats* s);
 
-int dmdb_run(dmdb_handle* h, int64_t n_events, dmdb_stats* stats) {
+static int run_impl(dmdb_handle* h, int64_t n_events, dmdb_stats* stats, int flags);
+int dmdb_run(dmdb_handle* h, int64_t n_events, dmdb_stats* stats) { return run_impl(h, n_events, stats, 0); }
+int dmdb_run_until_output(dmdb_handle* h, int64_t max_events, dmdb_stats* stats) { return run_impl(h, max_events, stats, 1); }
+
+static int run_impl(dmdb_handle* h, int64_t n_events, dmdb_stats* stats, int flags) {
   int rc = all_loaded(h);
   if (rc) return rc;
   if (n_events < 0) return fail(h, DMDB_ERR_ARG, "n_events must be >= 0");
@@ -299,7 +303,7 @@ int dmdb_run(dmdb_handle* h, int64_t n_events, dmdb_stats* stats) {
   if (engine == 0) engine = h->d.n_replicas >= 1184 ? 1 : 2;
   if (engine == 2 && !be::block_engine_fits(h->model.sys)) engine = 1;
   DMDB_TRY(h, be::run_op(h->d, engine == 2 ? dmd::OP_RUN_BLOCK : dmd::OP_RUN, 0, h->d.n_replicas, n_events, nullptr,
-                         nullptr, &h->last_ms, &h->last_launches);)
+                         nullptr, &h->last_ms, &h->last_launches, flags);)
   rc = check_device_errors(h);
   if (rc) return rc;
   if (stats) return dmdb_get_replica_stats(h, -1, stats);

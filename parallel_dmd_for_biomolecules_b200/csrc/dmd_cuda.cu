@@ -73,14 +73,14 @@ __device__ __forceinline__ int replica_of_warp(int r0, int nrep) {
   return w < nrep ? r0 + w : -1;
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, DMD_MIN_CTAS) dmd_event_loop_kernel(DevArrays d, int r0, int nrep, long long n_events) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, DMD_MIN_CTAS) dmd_event_loop_kernel(DevArrays d, int r0, int nrep, long long n_events, int flags) {
   __shared__ SmemConsts sconst;
   const Staged tab = stage_consts(d, &sconst);
   int rid = replica_of_warp(r0, nrep);
   if (rid < 0) return;
   Rep r;
   rep_bind(r, d, tab, warp_queue(), rid);
-  if (r.error == 0) run_events(r, n_events);
+  if (r.error == 0) run_events(r, n_events, (flags & 1) != 0);
   rep_save(r);
 }
 
@@ -110,7 +110,7 @@ __host__ __device__ inline BlkLayout blk_layout(int N, int cal_stride, size_t li
 }
 
 __global__ void __launch_bounds__(BK_MAXW * 32, 1) dmd_block_loop_kernel(DevArrays d, int r0, int nrep, long long n_events,
-                                                                         unsigned smem_limit) {
+                                                                         unsigned smem_limit, int flags) {
   extern __shared__ __align__(128) unsigned char blk_smem[];
   const int N = d.sys->N;
   const BlkLayout L = blk_layout(N, d.cal_stride, smem_limit);
@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(BK_MAXW * 32, 1) dmd_block_loop_kernel(DevArra
     if (tid == 0) {
       S.coll = r.coll;
       S.target = r.coll + n_events;
+      S.stop_at_output = flags & 1;
       S.window = r.interval * 0.02;
       S.error = r.error;
       S.error_info = r.error_info;
@@ -504,7 +505,7 @@ inline void run_pack(const dmd::DevArrays& d, double* sv, int32_t* bp) {
 
 // one launcher per device operation; times the kernel with CUDA events on the launching stream
 inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long arg, int32_t* ibuf, dmd::OutRec* eout,
-                   double* ms, int* launches) {
+                   double* ms, int* launches, int flags = 0) {
   using namespace dmd;
   const int block = WARPS_PER_CTA * 32;
   const int grid = (nrep + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
@@ -514,7 +515,7 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
     case 0: launch_nbor(d, r0, nrep); launch_predict_all(d, r0, nrep); nl = 5; break;
     case 1: launch_nbor(d, r0, nrep); nl = 3; break;
     case 2: launch_predict_all(d, r0, nrep); nl = 2; break;
-    case 3: dmd_event_loop_kernel<<<grid, block, 0, g_stream>>>(d, r0, nrep, arg); break;
+    case 3: dmd_event_loop_kernel<<<grid, block, 0, g_stream>>>(d, r0, nrep, arg, flags); break;
     case 4: dmd_sync_positions_kernel<<<grid, block, 0, g_stream>>>(d, r0, nrep); break;
     case 5: dmd_energy_kernel<<<grid, block, 0, g_stream>>>(d, r0, nrep, eout); break;
     case 6: dmd_evcode_kernel<<<((int)arg + 127) / 128, 128, 0, g_stream>>>(d, r0, (int)arg, ibuf); break;
@@ -527,7 +528,7 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
       if (L.total > smem_optin()) throw std::runtime_error("system too large for the CTA-per-replica engine");
       CUDA_OK(cudaFuncSetAttribute(dmd_block_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
       const int g = nrep < sms ? nrep : sms;
-      dmd_block_loop_kernel<<<g, BK_MAXW * 32, L.total, g_stream>>>(d, r0, nrep, arg, (unsigned)smem_optin());
+      dmd_block_loop_kernel<<<g, BK_MAXW * 32, L.total, g_stream>>>(d, r0, nrep, arg, (unsigned)smem_optin(), flags);
       break;
     }
     default: throw std::runtime_error("unknown device op");

@@ -1223,21 +1223,26 @@ DMD_DEV void process_one(Rep& r, int o, const CalEnt& ev) {
   r.old_tfalse = r.tfalse;
 }
 
-DMD_DEV bool step(Rep& r) {
+// returns the owner index of the processed calendar entry, or -1 on error
+DMD_DEV int step(Rep& r) {
   flush_dirty(r);
   CalEnt ev;
   const int o = pop_min(r, ev);
   if (o < 0) {
     set_error(r, DMD_E_CAL_EMPTY, 0);
-    return false;
+    return -1;
   }
   process_one(r, o, ev);
-  return r.error == 0;
+  return r.error == 0 ? o : -1;
 }
 
-DMD_DEV void run_events(Rep& r, int64_t n_events) {
-  for (int64_t n = 0; n < n_events; n++)
-    if (!step(r)) break;
+// stop_at_output: return right after the output pseudo-event (main.F90:1191-1246) has been processed, so that the
+// host can write the .energy line and the .config / .bptnr / .lastvel records exactly where the reference does
+DMD_DEV void run_events(Rep& r, int64_t n_events, bool stop_at_output) {
+  for (int64_t n = 0; n < n_events; n++) {
+    const int o = step(r);
+    if (o < 0 || (stop_at_output && o == r.N + 2)) break;
+  }
   flush_dirty(r);
 }
 

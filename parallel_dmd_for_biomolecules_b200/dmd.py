@@ -27,7 +27,7 @@ SYMBOLS = [
     "dmdb_set_temperature", "dmdb_nbor", "dmdb_predict_all", "dmdb_run", "dmdb_sync_positions", "dmdb_get_cells",
     "dmdb_get_nbors", "dmdb_get_calendar", "dmdb_get_state", "dmdb_get_evcode", "dmdb_energy_of",
     "dmdb_get_event_log", "dmdb_get_replica_stats", "dmdb_potential_energies", "dmdb_set_state_all",
-    "dmdb_get_state_all", "dmdb_apply_temperatures", "dmdb_get_batch_stats",
+    "dmdb_get_state_all", "dmdb_apply_temperatures", "dmdb_get_batch_stats", "dmdb_run_until_output",
 ]
 
 
@@ -140,6 +140,12 @@ class DMD:
         """the main loop main.F90:484-1258: every replica processes ``n_events`` calendar events"""
         s = Stats()
         self._chk(self._l.dmdb_run(self._h, C.c_int64(n_events), C.byref(s)))
+        return s
+
+    def run_until_output(self, max_events: int) -> Stats:
+        """like run(), but returns right after the next output pseudo-event (main.F90:1191-1246)"""
+        s = Stats()
+        self._chk(self._l.dmdb_run_until_output(self._h, C.c_int64(max_events), C.byref(s)))
         return s
 
     def sync_positions(self):

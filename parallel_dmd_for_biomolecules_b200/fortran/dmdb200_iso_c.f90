@@ -18,7 +18,7 @@ module dmdb200
   public :: dmdb_params, dmdb_tables, dmdb_topology, dmdb_stats, dmdb_energy, dmdb_event
   public :: dmdb_create, dmdb_destroy, dmdb_last_error, dmdb_num_beads, dmdb_num_cells
   public :: dmdb_set_state, dmdb_set_state_all, dmdb_get_state_all, dmdb_set_temperature
-  public :: dmdb_nbor, dmdb_predict_all, dmdb_run, dmdb_sync_positions
+  public :: dmdb_nbor, dmdb_predict_all, dmdb_run, dmdb_run_until_output, dmdb_sync_positions
   public :: dmdb_get_cells, dmdb_get_nbors, dmdb_get_calendar, dmdb_get_state, dmdb_get_evcode
   public :: dmdb_energy_of, dmdb_get_event_log, dmdb_get_replica_stats
   public :: dmdb_potential_energies, dmdb_apply_temperatures, dmdb_get_batch_stats
@@ -153,6 +153,14 @@ module dmdb200
       import :: c_ptr, c_int, c_int64_t, dmdb_stats
       type(c_ptr), value :: handle
       integer(c_int64_t), value :: n_events
+      type(dmdb_stats), intent(out) :: stats
+      integer(c_int) :: rc
+    end function
+    ! the same loop, returning right after the next output pseudo-event (main.F90:1191-1246)
+    function dmdb_run_until_output(handle, max_events, stats) bind(C, name="dmdb_run_until_output") result(rc)
+      import :: c_ptr, c_int, c_int64_t, dmdb_stats
+      type(c_ptr), value :: handle
+      integer(c_int64_t), value :: max_events
       type(dmdb_stats), intent(out) :: stats
       integer(c_int) :: rc
     end function

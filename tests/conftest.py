@@ -72,3 +72,27 @@ def compare_engines(ora, dev, replica=0, n_events=0, time_rtol=1e-12):
         for f in ("bptnr", "identity", "extra_repuls"):
             assert np.array_equal(sa[f], sb[f]), f
         assert sa["coll"] == sb["coll"]
+
+
+def check_run_until_output(tab, engines, lib_path=None):
+    from parallel_dmd_for_biomolecules_b200.dmd import DMD
+    topo, sv = genconfig.generate_box(["AAAA"], [2], 40.0, 0.5, tab, seed=2)
+    N = topo.n_beads
+    stops = []
+    for engine in engines:
+        p = tables.make_params(boxl=40.0, tstar=0.5, canon=True, n_replicas=1, log_capacity=4, engine=engine, seed=7)
+        with DMD(p, topo, tab, lib_path=lib_path) as d:
+            d.set_state(sv)
+            budget = 20_000_000
+            d.run_until_output(budget)
+            st = d.state(0)
+            assert 0 < st["coll"] < budget
+            tim, nptnr, coltype = d.calendar(0)
+            period = 3.3 / np.sqrt(6.0) + 5
+            assert abs((tim[N + 2] - st["tfalse"]) - period) < 1e-9  # the output event has just re-armed itself
+            assert abs(st["t"] + st["tfalse"] - period) < 1e-6       # ... at the first output time
+            stops.append((st["coll"], st["t"] + st["tfalse"]))
+            d.run(1000)
+            assert d.state(0)["coll"] == st["coll"] + 1000
+    assert all(s == stops[0] for s in stops)
+    return stops[0]

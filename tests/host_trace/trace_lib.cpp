@@ -31,7 +31,7 @@ static int trace_block_warps() {
   return n < 1 ? 1 : (n > BK_MAXW ? BK_MAXW : n);
 }
 
-static void trace_run_block(const DevArrays& d, int rid, long long n_events) {
+static void trace_run_block(const DevArrays& d, int rid, long long n_events, int flags) {
   const int nw = trace_block_warps();
   const int N = d.sys->N;
   BlkShared* S = new BlkShared();
@@ -45,6 +45,7 @@ static void trace_run_block(const DevArrays& d, int rid, long long n_events) {
     rep_bind(r0, d, staged_global(d), cq.data(), rid);
     S->coll = r0.coll;
     S->target = r0.coll + n_events;
+    S->stop_at_output = flags & 1;
     S->window = r0.interval * 0.02;
     S->tlast = -1.0;
     S->error = r0.error;
@@ -117,7 +118,7 @@ inline void run_pack(const dmd::DevArrays& d, double* sv, int32_t* bp) {
   }
 }
 inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long arg, int32_t* ibuf, dmd::OutRec* eout,
-                   double* ms, int* launches) {
+                   double* ms, int* launches, int flags = 0) {
   using namespace dmd;
   if (op == 6) {
     const int N = d.sys->N, n_pairs = (int)arg;
@@ -140,8 +141,8 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
           break;
         case 1: nbor(r); rep_save(r); break;
         case 2: predict_all(r); rep_save(r); break;
-        case 3: if (r.error == 0) run_events(r, arg); rep_save(r); break;
-        case 8: if (r.error == 0) trace_run_block(d, rid, arg); break;
+        case 3: if (r.error == 0) run_events(r, arg, (flags & 1) != 0); rep_save(r); break;
+        case 8: if (r.error == 0) trace_run_block(d, rid, arg, flags); break;
         case 4: sync_positions(r); break;
         case 5: { OutRec o; energy_of(r, o); eout[rid] = o; } break;
         case 7: { double tn = ((const double*)ibuf)[rid]; if (tn > 0.0) { retemp(r, tn); rep_save(r); } } break;

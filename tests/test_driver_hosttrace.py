@@ -1,0 +1,60 @@
+"""Run driver (driver.py = what one `./dmd < temp_0xx` does around the loop): run numbering and restart chaining
+(files_opn.f:19-46, inputinfo.f:79-101), record formats (config.f:16-40), the .energy line (main.F90:1380).
+Runs on the CPU through the host-trace build of the engine (test scaffolding)."""
+import os
+import shutil
+
+import numpy as np
+
+from conftest import GOLDEN
+from parallel_dmd_for_biomolecules_b200 import driver, fileio, tables
+
+
+def test_two_chained_runs_write_reference_style_files(tmp_path, tab, system_a, hosttrace_lib):
+    topo, sv, boxl = system_a
+    res = tmp_path / "results"
+    res.mkdir()
+    # what genconfig leaves behind: run0000.config/.lastvel plus EMPTY run0000.energy/.bptnr
+    shutil.copy(os.path.join(GOLDEN, "systemA_run0000.config"), res / "run0000.config")
+    shutil.copy(os.path.join(GOLDEN, "systemA_run0000.lastvel"), res / "run0000.lastvel")
+    (res / "run0000.energy").write_text("")
+    (res / "run0000.bptnr").write_bytes(b"")
+    # a short output period is not configurable (it is the reference's 3.3/sqrt(setemp)+5): events only
+    s1 = driver.run_temperature(str(tmp_path), topo, tab, 0.5, 30000, boxl=boxl, lib_path=hosttrace_lib)
+    assert s1["run"] == 1 and s1["events"] == 30000
+    lines = (res / "run0001.energy").read_text().splitlines()
+    assert len(lines) == s1["energy_lines"] >= 2
+    assert all(len(ln) == 15 + 3 * 12 + 3 * 8 + 4 * 12 for ln in lines)  # (i15,3f12.4,3i8,4f12.4)
+    assert int(lines[0][:15]) == 0 and int(lines[-1][:15]) == 29999
+    coll, t, xyz = fileio.read_config(str(res / "run0001.config"))
+    assert coll == 30000 and xyz.shape == (3, topo.n_beads) and np.abs(xyz).max() <= 0.5 and t > 0
+    c2, vel = fileio.read_lastvel(str(res / "run0001.lastvel"))
+    assert c2 == 30000 and vel.shape == (3, topo.n_beads)
+    # temperature of the written velocities equals the last energy line's T column
+    from parallel_dmd_for_biomolecules_b200 import genconfig
+    m = genconfig.masses_of(topo, tab)
+    tred = float((m * (vel ** 2).sum(axis=0)).sum() / 3.0 / topo.n_beads)
+    assert abs(tred - float(lines[-1][15 + 24:15 + 36])) < 1e-3
+    # second run restarts from run0001 and becomes run0002
+    s2 = driver.run_temperature(str(tmp_path), topo, tab, 0.45, 10000, boxl=boxl, lib_path=hosttrace_lib)
+    assert s2["run"] == 2
+    coll0, t0, xyz0 = fileio.read_config(str(res / "run0001.config"))
+    sv2 = fileio.sv_from_files(str(res / "run0001.config"), str(res / "run0001.lastvel"))
+    assert np.array_equal(sv2[:, :3].T, xyz0)
+    assert os.path.exists(res / "run0002.energy") and os.path.getsize(res / "run0002.config") > 0
+    assert driver.first_unused_run(str(res)) == 3
+
+
+def test_observables_on_the_shipped_snapshot(tab, system_a):
+    topo, sv, boxl = system_a
+    rg = driver.radgyr(topo, sv[:, :3], boxl)
+    e2e = driver.end_to_end(topo, sv[:, :3], boxl)
+    # an extended 22-residue chain: Ca-Ca 3.8 A -> end-to-end of the order of 70 A, backbone Rg of the order of 20 A
+    assert 55.0 < e2e < 85.0 and 15.0 < rg < 30.0
+
+
+def test_run_until_output_stops_right_after_the_output_event(tab, hosttrace_lib):
+    """A tiny box reaches the first output pseudo-event (3.3/sqrt(setemp)+5 time units, main.F90:423) within a few
+    hundred thousand events: the run stops right after it and can go on.  (Both engines: tests/test_gpu_parity.py.)"""
+    from conftest import check_run_until_output
+    check_run_until_output(tab, [1], hosttrace_lib)

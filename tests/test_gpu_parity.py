@@ -104,6 +104,13 @@ def test_engines_alternate_on_one_handle(tab, system_b):
     assert np.array_equal(ora.state()["sv"], dev.state(0)["sv"])
 
 
+def test_run_until_output_both_engines(tab):
+    """dmdb_run_until_output: both engines stop right after the first output pseudo-event, at the same event."""
+    from conftest import check_run_until_output
+    coll, t = check_run_until_output(tab, [1, 2])
+    assert coll > 1000
+
+
 def test_retemp_and_distinct_states(tab, system_b):
     topo, sv, boxl = system_b
     p = tables.make_params(boxl=boxl, tstar=0.18, canon=True, n_replicas=3, log_capacity=40000)
