@@ -165,7 +165,8 @@ int dmdb_get_replica_stats(dmdb_handle* h, int replica, dmdb_stats* s);
 /* Batching statistics of the CTA-per-replica engine (summed over replicas when replica = -1): out[0] rounds,
  * [1] events executed speculatively, [2] of those rolled back (main.F90:970-993 rule), [3] candidates dropped by a
  * footprint conflict, [4] events processed serially at the head (H-bond events, pseudo-events), [5..7] reserved,
- * [8..14] SM clock cycles spent in the phases scan / select+sort / claim / check / exec / commit / serial. */
+ * [8..15] SM clock cycles spent in the phases scan / select+rank / claim / check / exec / commit / serial head
+ * events / of which list rebuilds. */
 int dmdb_get_batch_stats(dmdb_handle* h, int replica, int64_t out[16]);
 
 /* Replica exchange (new functionality, no reference counterpart): gathers (E_pot, T*) of the local replicas.

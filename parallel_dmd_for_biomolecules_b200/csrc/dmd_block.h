@@ -89,7 +89,8 @@ struct BlkShared {
   CalEnt undo_old[BK_MAXW][BK_UNDO];
   int32_t undo_idx[BK_MAXW][BK_UNDO];
   uint32_t fp[BK_MAXW][4][FP_SIDE];  // staged lists of the slot's event: up(i), dn(i), up(j), dn(j)
-  long long cyc[8];                  // clock64 per phase (thread 0): scan, select+sort, claim, check, exec, commit, serial
+  long long cyc[8];                  // clock64 per phase (thread 0): scan, select+rank, claim, check, exec, commit, serial
+                                     // head events, of which list rebuilds
 };
 
 #if defined(DMD_HOST_TRACE)
@@ -395,12 +396,34 @@ __device__ __noinline__ void blk_interval_event(BlkShared& S, Rep& r, int w, int
       r.oldr[3 * k] = x; r.oldr[3 * k + 1] = y; r.oldr[3 * k + 2] = z;
     }
     __syncthreads();
-    cell_build(r, tid, nt);
-    __syncthreads();
-    nbor_build(r, tid, nt);
-    __syncthreads();
-    cell_clear(r, tid, nt);
+    const long long tr = blk_clock();
+    {
+      // the cell grid of the rebuild lives in the (idle) undo / footprint buffers when it fits: list heads of the
+      // coarse grid, chain links and packed cell coordinates then cost a shared-memory access per hop instead of
+      // an L2 round trip (the walk is a chain of dependent loads)
+      Rep q = r;
+      const int ncc = coarse_dim(s.ncr);
+      const size_t nheads = (size_t)ncc * ncc * ncc;
+      const size_t avail = sizeof(S.undo_old) + sizeof(S.undo_idx) + sizeof(S.fp);  // consecutive members
+      const bool fits = (nheads + 2 * (size_t)N) * 4 <= avail;
+      if (fits) {
+        int32_t* scratch = reinterpret_cast<int32_t*>(&S.undo_old[0][0]);
+        q.cellhead = scratch;
+        q.cnext = scratch + nheads;
+        q.cpk = reinterpret_cast<uint32_t*>(scratch + nheads + N);
+        for (size_t k = tid; k < nheads; k += nt) scratch[k] = -1;
+        __syncthreads();
+      }
+      cell_build(q, tid, nt);
+      __syncthreads();
+      nbor_build(q, tid, nt);
+      __syncthreads();
+      if (!fits) cell_clear(q, tid, nt);
+      if (q.error) set_error(r, q.error, q.error_info);
+    }
     for (int l = tid; l < N; l += nt) redo_lane(r, l);  // events(): every bead from interval_max + ltstep
+    __syncthreads();
+    if (tid == 0) S.cyc[7] += blk_clock() - tr;
     if (r.error && Warp::lane() == 0) {
       S.error = r.error;
       S.error_info = r.error_info;

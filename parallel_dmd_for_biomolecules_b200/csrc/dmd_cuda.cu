@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(BK_MAXW * 32, 1) dmd_block_loop_kernel(DevArra
         for (int q = 0; q < 32; q++) r.sc->nevents[q] += S.nevents[q];
         long long* st = d.blkstat + (size_t)rid * 16;
         st[0] += S.st_rounds; st[1] += S.st_exec; st[2] += S.st_rollback; st[3] += S.st_conflict; st[4] += S.st_cold;
-        for (int q = 0; q < 7; q++) st[8 + q] += S.cyc[q];
+        for (int q = 0; q < 8; q++) st[8 + q] += S.cyc[q];
       }
     }
     __syncthreads();

@@ -219,7 +219,7 @@ class DMD:
         out = (C.c_int64 * 16)()
         self._chk(self._l.dmdb_get_batch_stats(self._h, replica, out))
         return dict(rounds=out[0], executed=out[1], rolled_back=out[2], conflicts=out[3], serial=out[4],
-                    cycles=dict(zip(("scan", "select_sort", "claim", "check", "exec", "commit", "serial"), list(out)[8:15])))
+                    cycles=dict(zip(("scan", "select_rank", "claim", "check", "exec", "commit", "serial", "rebuild"), list(out)[8:16])))
 
     def stats(self, replica=-1) -> Stats:
         s = Stats()
