@@ -328,7 +328,7 @@ def main():
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "path": "dmdb_set_state_all(pinned host sv,bptnr) -> dmdb_run -> dmdb_sync_positions -> "
                             "dmdb_get_state_all + dmdb_potential_energies"},
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps * (1 + (2 if world > 1 else 0)),  # event loop (+ energy and retemp kernels of the exchange)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "dmd_event_loop_kernel",
                          "algorithmic_bytes_per_launch": abytes / args.steps,
