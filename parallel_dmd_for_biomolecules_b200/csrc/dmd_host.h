@@ -247,6 +247,7 @@ inline void build_model(const dmdb_params& p, const dmdb_topology& topo, const d
   std::memcpy(m.hot.ev_param3, s.ev_param3, sizeof(s.ev_param3));
   std::memcpy(m.hot.sqz610, s.sqz610, sizeof(s.sqz610));
   std::memcpy(m.hot.bmass, s.bmass, sizeof(s.bmass));
+  for (int id = 0; id < 29; id++) m.hot.binv[id] = s.bmass[id] != 0.0 ? 1.0 / s.bmass[id] : 0.0;
   m.hot.chnln0 = s.chnln[0];
   m.hot.nres = s.chnln[0] + (topo.n_species == 2 ? s.chnln[1] : 0);
   m.bl.assign((size_t)m.hot.nres * 6, 0.0);

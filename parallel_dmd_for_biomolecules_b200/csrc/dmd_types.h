@@ -71,6 +71,7 @@ struct HotConst {
   double ev_param3[51];
   double sqz610[5 * 29];
   double bmass[29];
+  double binv[29];  // RN(1 / bmass): lets a division by a mass be done exactly with 5 multiply-adds (dmd_physics.h)
   int32_t chnln0, nres;
 };
 

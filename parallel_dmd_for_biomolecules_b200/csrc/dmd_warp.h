@@ -30,6 +30,7 @@ DMD_DEV int dmd_ffs(unsigned m) { return __builtin_ffs((int)m); }
 DMD_DEV int dmd_popc(unsigned m) { return __builtin_popcount(m); }
 DMD_DEV double dmd_sqrt(double x) { return std::sqrt(x); }
 DMD_DEV double dmd_round(double x) { return std::round(x); }
+DMD_DEV double dmd_fma(double a, double b, double c) { return std::fma(a, b, c); }
 DMD_DEV double dmd_hi_lo(int hi, unsigned lo) {
   uint64_t b = ((uint64_t)(uint32_t)hi << 32) | lo;
   double d;
@@ -68,6 +69,7 @@ DMD_DEV int dmd_ffs(unsigned m) { return __ffs((int)m); }
 DMD_DEV int dmd_popc(unsigned m) { return __popc(m); }
 DMD_DEV double dmd_sqrt(double x) { return sqrt(x); }    // IEEE-exact fp64 sqrt on device
 DMD_DEV double dmd_round(double x) { return round(x); }  // round half away from zero == Fortran dnint
+DMD_DEV double dmd_fma(double a, double b, double c) { return __fma_rn(a, b, c); }  // explicit: -fmad=false stays on
 DMD_DEV double dmd_hi_lo(int hi, unsigned lo) { return __hiloint2double(hi, (int)lo); }
 DMD_DEV int dmd_hi(double d) { return __double2hiint(d); }
 DMD_DEV unsigned dmd_lo(double d) { return (unsigned)__double2loint(d); }
