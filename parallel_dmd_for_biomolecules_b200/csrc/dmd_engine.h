@@ -25,7 +25,10 @@
 namespace dmd {
 
 constexpr double T_PAD = 1e300;  // calendar padding entries
-constexpr int CQ_CAP = 160;      // cascade queue (<= one entry per down-list candidate of a pass)
+#ifndef DMD_CQ_CAP
+#define DMD_CQ_CAP 160
+#endif
+constexpr int CQ_CAP = DMD_CQ_CAP;  // cascade queue (<= one entry per down-list candidate of the two main passes)
 
 struct Rep {
   Ctx c;

@@ -124,3 +124,30 @@ def test_capacity_error_is_reported(tab, system_b, hosttrace_lib):
     with pytest.raises(DMDError) as e:
         dev.set_state(sv)
     assert e.value.code == 5 and "capacity" in str(e.value)
+
+
+@pytest.mark.parametrize("engine", [1, 2])
+def test_ragged_two_species_box_with_gly(tab, hosttrace_lib, engine):
+    """Two species of different length with glycines (no side-chain bead) in one box, with and without the -Dno_hbs
+    build flag: same committed-event sequence as the oracle.  (Proline topologies: test_static_evcode_*.)"""
+    for no_hbs in (False, True):
+        topo, sv = genconfig.generate_box(["GAKLGVFE", "GAAKGS"], [3, 4], 60.0, 0.35, tab, seed=4)
+        n = 40000
+        p = tables.make_params(boxl=60.0, tstar=0.35, canon=True, no_hbs=no_hbs, n_replicas=1, log_capacity=n, seed=21,
+                               engine=engine)
+        ora, dev = _pair(p, topo, tab, sv, hosttrace_lib)
+        compare_engines(ora, dev, n_events=n)
+        assert not ora.checkover()[0]
+
+
+def test_box_too_small_and_bad_bptnr_are_errors(tab, hosttrace_lib):
+    from parallel_dmd_for_biomolecules_b200.dmd import DMDError
+    topo, sv = genconfig.generate_box(["AAAA"], [2], 40.0, 0.5, tab, seed=2)
+    with pytest.raises(DMDError):  # fewer than 5 cells per dimension (main.F90:390)
+        DMD(tables.make_params(boxl=7.0, tstar=0.5), topo, tab, lib_path=hosttrace_lib)
+    d = DMD(tables.make_params(boxl=40.0, tstar=0.5), topo, tab, lib_path=hosttrace_lib)
+    bad = np.zeros(topo.n_beads, dtype=np.int32)
+    bad[3] = topo.n_beads + 5
+    with pytest.raises(DMDError) as e:
+        d.set_state(sv, bad)
+    assert e.value.code == 1  # DMDB_ERR_ARG

@@ -104,6 +104,25 @@ def test_engines_alternate_on_one_handle(tab, system_b):
     assert np.array_equal(ora.state()["sv"], dev.state(0)["sv"])
 
 
+@pytest.mark.parametrize("engine", [1, 2])
+def test_ragged_two_species_box_with_gly(tab, engine):
+    """Two species of different length with glycines, with and without -Dno_hbs: the oracle's sequence; and the run
+    is deterministic (a second handle started from the same state repeats it bit for bit)."""
+    for no_hbs in (False, True):
+        topo, sv = genconfig.generate_box(["GAKLGVFE", "GAAKGS"], [3, 4], 60.0, 0.35, tab, seed=4)
+        n = 60000
+        p = tables.make_params(boxl=60.0, tstar=0.35, canon=True, no_hbs=no_hbs, n_replicas=3, log_capacity=n, seed=21,
+                               engine=engine)
+        ora, dev = _pair(p, topo, tab, sv)
+        compare_engines(ora, dev, n_events=n)
+        dev2 = DMD(p, topo, tab)
+        dev2.set_state(sv)
+        dev2.run(n)
+        for r in range(3):
+            assert np.array_equal(dev.event_log(r), dev2.event_log(r))
+            assert np.array_equal(dev.state(r)["sv"], dev2.state(r)["sv"])
+
+
 def test_run_until_output_both_engines(tab):
     """dmdb_run_until_output: both engines stop right after the first output pseudo-event, at the same event."""
     from conftest import check_run_until_output
