@@ -135,25 +135,24 @@ DMD_DEV void blk_footprint(const Rep& r, int i, int j, const ListRef& li, const 
   }
 }
 
-// the two lists of bead a: staged into the slot's shared-memory buffer when they fit (the passes of the event
-// then never go to global memory for them), else left where they are
-DMD_DEV ListRef blk_stage_lists(const Rep& r, int a, uint32_t* sup, uint32_t* sdn) {
-  ListRef l;
-  l.nu = r.nup[a];
-  l.nd = r.ndn[a];
-  const size_t lbase = (size_t)a * r.cap;
-  if (l.nu <= FP_SIDE && l.nd <= FP_SIDE) {
-    for (int p = Warp::lane(); p < FP_SIDE; p += DMD_W) {
-      sup[p] = p < l.nu ? r.up[lbase + p] : 0u;
-      sdn[p] = p < l.nd ? r.dn[lbase + p] : 0u;
-    }
-    l.up = sup;
-    l.dn = sdn;
-  } else {
-    l.up = r.up + lbase;
-    l.dn = r.dn + lbase;
+// the lists of the event's two beads: staged into the slot's shared-memory buffers when they fit (the passes of
+// the event then never go to global memory for them), else left where they are.  All eight loads of a lane (four
+// list entries, four lengths) are independent and issued together.
+DMD_DEV void blk_stage_lists(const Rep& r, int i, int j, uint32_t (*fp)[FP_SIDE], ListRef& li, ListRef& lj) {
+  li.nu = r.nup[i]; li.nd = r.ndn[i];
+  lj.nu = r.nup[j]; lj.nd = r.ndn[j];
+  const size_t bi = (size_t)i * r.cap, bj = (size_t)j * r.cap;
+  const bool fit_i = li.nu <= FP_SIDE && li.nd <= FP_SIDE, fit_j = lj.nu <= FP_SIDE && lj.nd <= FP_SIDE;
+  for (int p = Warp::lane(); p < FP_SIDE; p += DMD_W) {
+    const bool in = p < r.cap;
+    const uint32_t a0 = in ? r.up[bi + p] : 0u, a1 = in ? r.dn[bi + p] : 0u;
+    const uint32_t a2 = in ? r.up[bj + p] : 0u, a3 = in ? r.dn[bj + p] : 0u;
+    fp[0][p] = a0; fp[1][p] = a1; fp[2][p] = a2; fp[3][p] = a3;
   }
-  return l;
+  li.up = fit_i ? fp[0] : r.up + bi;
+  li.dn = fit_i ? fp[1] : r.dn + bi;
+  lj.up = fit_j ? fp[2] : r.up + bj;
+  lj.dn = fit_j ? fp[3] : r.dn + bj;
 }
 
 // ---- scan + select in one sweep: per-warp arg-min over a block-strided slice of the calendar, and every entry
@@ -185,11 +184,11 @@ DMD_DEV void blk_phase_scan(BlkShared& S, const Rep& r, int w, int nw, double li
   }
 }
 
-DMD_DEV double blk_tmin(const BlkShared& S, int nw) {
-  double t = S.wmin_t[0];
-  for (int q = 1; q < nw; q++)
+DMD_DEV double blk_tmin(const BlkShared& S, int nw) {  // redundant per warp
+  double t = T_PAD;
+  for (int q = Warp::lane(); q < nw; q += DMD_W)
     if (S.wmin_t[q] < t) t = S.wmin_t[q];
-  return t;
+  return warp_min(t);
 }
 
 // ---- rank by (time, owner index) = the serial processing order (oracle decision D3): all pairs in parallel
@@ -226,8 +225,7 @@ DMD_DEV void blk_phase_claim(BlkShared& S, const Rep& r, uint32_t* claim, int w,
   const int k = blk_cand_of_rank(S, nc, w);
   const int i = S.cand_o[k];
   const int j = r.cal[i].ptnr;
-  li = blk_stage_lists(r, i, S.fp[w][0], S.fp[w][1]);
-  lj = blk_stage_lists(r, j, S.fp[w][2], S.fp[w][3]);
+  blk_stage_lists(r, i, j, S.fp[w], li, lj);
   Warp::sync();
   blk_footprint(r, i, j, li, lj, [&](int b) { blk_atomic_min(&claim[b], (uint32_t)w); });
   if (Warp::lane() == 0) {
@@ -254,10 +252,11 @@ DMD_DEV void blk_phase_check(BlkShared& S, const Rep& r, const uint32_t* claim, 
   if (Warp::lane() == 0 && any_bad) S.slot[w].win = 0;
 }
 
-DMD_DEV int blk_n_exec(const BlkShared& S, int batch) {  // redundant per thread
-  int n = 0;
-  while (n < batch && S.slot[n].win) n++;
-  return n;  // >= 1: rank 0 holds the minimum stamp everywhere
+DMD_DEV int blk_n_exec(const BlkShared& S, int batch) {  // redundant per warp: first slot that lost a claim
+  int first_lost = batch;
+  for (int q = Warp::lane(); q < batch; q += DMD_W)
+    if (!S.slot[q].win && q < first_lost) first_lost = q;
+  return warp_min_i(first_lost);  // >= 1: rank 0 holds the minimum stamp everywhere
 }
 
 // ---- exec: one hot pair event (main.F90:1636 eventdyn + :943 partial_events) with undo logging
@@ -308,8 +307,23 @@ DMD_DEV void blk_rollback(BlkShared& S, Rep& r, int w) {
   }
 }
 
-// reference's validation rule (main.F90:970-993): event q is kept iff every event created by 0..q-1 is later
-DMD_DEV int blk_n_valid(const BlkShared& S, int n_exec) {  // redundant per thread
+// reference's validation rule (main.F90:970-993): event q is kept iff every event created by 0..q-1 is later.
+// Redundant per warp; lane q holds slot q (n_exec <= BK_MAXW <= 32).
+DMD_DEV int blk_n_valid(const BlkShared& S, int n_exec) {
+#if DMD_W > 1
+  const int q = Warp::lane();
+  const double t = q < n_exec ? S.slot[q].t : T_PAD;
+  double pm = q < n_exec ? S.slot[q].newmin : T_PAD;  // -> inclusive prefix minimum of newmin
+#pragma unroll
+  for (int d = 1; d < BK_MAXW; d <<= 1) {
+    const double o = Warp::shfl(pm, q >= d ? q - d : q);
+    if (q >= d && o < pm) pm = o;
+  }
+  const double before = Warp::shfl(pm, q > 0 ? q - 1 : 0);  // minimum over slots 0..q-1
+  const bool bad = q > 0 && q < n_exec && !(t < before);
+  const unsigned m = Warp::ballot(bad);
+  return m ? dmd_ffs(m) - 1 : n_exec;
+#else
   double rm = S.slot[0].newmin;
   int v = 1;
   while (v < n_exec && S.slot[v].t < rm) {
@@ -317,17 +331,28 @@ DMD_DEV int blk_n_valid(const BlkShared& S, int n_exec) {  // redundant per thre
     v++;
   }
   return v;
+#endif
 }
 
-// warp 0: account for the committed events in serial order (main.F90:639, 926) and log them
+// warp 0: account for the committed events in serial order (main.F90:639, 926) and log them; lane q takes slot q
 DMD_DEV void blk_commit(BlkShared& S, Rep& r, int n_valid) {
-  for (int q = 0; q < n_valid; q++) {
+  const int log_cap = r.c.sys->log_cap;
+  for (int q = Warp::lane(); q < n_valid; q += DMD_W) {
     const BlkSlot& sl = S.slot[q];
-    r.tfalse = sl.t;
-    r.coll += 1;
-    if (Warp::lane() == 0 && sl.ct >= 0 && sl.ct < 32) S.nevents[sl.ct] += 1;
-    log_event(r, sl.owner, sl.j, sl.ct, sl.code);
+    if (sl.ct >= 0 && sl.ct < 32) blk_atomic_add64(&S.nevents[sl.ct], 1);
+    if (r.n_log + q < log_cap) {
+      EventLogRec e;
+      e.t = r.t + sl.t;
+      e.i = sl.owner + 1;
+      e.j = sl.j + 1;
+      e.type = sl.ct;
+      e.evcode = sl.code;
+      r.log[r.n_log + q] = e;
+    }
   }
+  if (r.n_log < log_cap) r.n_log = r.n_log + n_valid < log_cap ? r.n_log + n_valid : log_cap;  // like log_event()
+  r.coll += n_valid;
+  r.tfalse = S.slot[n_valid - 1].t;
   r.old_tfalse = r.tfalse;
 }
 
