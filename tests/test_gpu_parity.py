@@ -198,3 +198,62 @@ def test_errors_are_reported_not_fatal(tab, system_b):
         dev2.run(10)  # no state loaded
     with pytest.raises(ValueError):
         dev2.set_state(sv[:10])
+
+
+@pytest.mark.parametrize("engine", [1, 2])
+def test_config4_12288_beads_matches_oracle(tab, engine):
+    """BASELINE config 4 (192 chains x 16 residues = 12 288 beads): too large for the shared-memory state of the
+    CTA-per-replica engine, which then works on the global arrays; cells, lists, calendar and 20 000 committed events
+    equal the oracle's."""
+    topo, sv = genconfig.generate_box(["KLVFFAEKLVFFAEKL"], [192], 200.0, 0.3, tab, seed=3)
+    assert topo.n_beads == 12288
+    p = tables.make_params(boxl=200.0, tstar=0.3, canon=True, n_replicas=2, log_capacity=20000, engine=engine)
+    ora, dev = _pair(p, topo, tab, sv)
+    compare_engines(ora, dev, n_events=20000)
+    if engine == 2:
+        st = dev.batch_stats(0)
+        assert (st["executed"] - st["rolled_back"]) / st["rounds"] > 8.0  # larger box, larger batches
+
+
+def test_config5_million_bead_box_bulk_kernels(tab):
+    """BASELINE config 5 (35 715 x KLVFFAE = 1 000 020 beads at the density of config 2): run start, nbor() and
+    events() on the whole GPU.  The oracle's run start is O(N^2), so the check is by size-independent properties:
+    up and down lists are transposes of each other, every listed partner of a bead with an event is on its up list,
+    bonded-class neighbours are complete (each backbone bead lists its covalent partners), T* is the generated one."""
+    nch = 35715
+    boxl = 158.54 * (nch / 48.0) ** (1.0 / 3.0)
+    topo, sv = genconfig.generate_box(["KLVFFAE"], [nch], boxl, 0.5, tab, seed=5)
+    N = topo.n_beads
+    assert N == 1000020
+    dev = DMD(tables.make_params(boxl=boxl, tstar=0.5, canon=True, n_replicas=1, engine=1, nbr_capacity=32), topo, tab)
+    dev.set_state(sv)
+    off, nb = dev.nbors(0)
+    offd, nbd = dev.nbors(0, True)
+    assert len(nb) == len(nbd) > 4 * N
+    i_of = np.repeat(np.arange(1, N + 1), np.diff(off))
+    j_of = np.repeat(np.arange(1, N + 1), np.diff(offd))
+    a = np.stack([i_of, nb], 1)
+    b = np.stack([nbd, j_of], 1)
+    assert np.array_equal(a[np.lexsort((a[:, 1], a[:, 0]))], b[np.lexsort((b[:, 1], b[:, 0]))])
+    assert (nb > i_of).all() and (nbd < j_of).all()
+    tim, nptnr, coltype = dev.calendar(0)
+    has = nptnr[:N] > 0
+    assert has.sum() > N // 2
+    # the predicted partner of bead i is one of its up-list entries
+    key = set(zip(i_of[:200000].tolist(), nb[:200000].tolist()))
+    idx = np.nonzero(has[: i_of[199999] - 1])[0][:20000]
+    assert all((int(k) + 1, int(nptnr[k])) in key for k in idx)
+    # covalent partners: Ca_r lists N_r (code 4) and C_r (code 5) -- bead order per chain: Ca x7, N x7, C x7, R x7
+    first = np.arange(0, 1000) * 28 + 1  # Ca of residue 1 of the first 1000 chains (1-based)
+    for ca in first[:200]:
+        ups = set(nb[off[ca - 1]:off[ca]].tolist())
+        assert ca + 7 in ups and ca + 14 in ups
+    e = dev.energy(0)
+    assert abs(e.tred - 6.0) < 1e-6 and e.hb_ii + e.hb_ij == 0
+    # lists rebuilt a second time are identical as sets; events() is idempotent
+    dev.nbor()
+    off2, nb2 = dev.nbors(0)
+    assert np.array_equal(off, off2) and np.array_equal(nb, nb2)
+    dev.events()
+    tim2, nptnr2, coltype2 = dev.calendar(0)
+    assert np.array_equal(tim, tim2) and np.array_equal(nptnr, nptnr2) and np.array_equal(coltype, coltype2)
