@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, DMD_MIN_CTAS) dmd_event_lo
 // dynamic shared memory: BlkShared | PairTables | cascade queues | claim[N+3] | (rec[N] | cal[stride] | er34[2N])
 struct BlkLayout {
   size_t tab, cq, claim, meta, nup, ndn, rec, cal, er34, total;
-  bool state;  // bead records / calendar / er34 resident in shared memory
+  bool topo;   // topology words and list lengths resident in shared memory
+  bool state;  // ... and bead records / calendar / er34 too
 };
 __host__ __device__ inline size_t blk_align(size_t x) { return (x + 127) & ~(size_t)127; }
 __host__ __device__ inline BlkLayout blk_layout(int N, int cal_stride, size_t limit) {
@@ -97,15 +98,17 @@ __host__ __device__ inline BlkLayout blk_layout(int N, int cal_stride, size_t li
   L.tab = off; off += blk_align(sizeof(SmemConsts));
   L.cq = off; off += blk_align((size_t)BK_MAXW * CQ_CAP * 4);
   L.claim = off; off += blk_align(((size_t)N + 3) * 4);
+  L.total = off;  // the part that must fit
   L.meta = off; off += blk_align((size_t)N * 4);
   L.nup = off; off += blk_align((size_t)N * 2);
   L.ndn = off; off += blk_align((size_t)N * 2);
-  L.rec = off;
-  size_t st = off + blk_align((size_t)N * sizeof(BeadRec));
-  L.cal = st; st += blk_align((size_t)cal_stride * sizeof(CalEnt));
-  L.er34 = st; st += blk_align((size_t)N * 8);
-  L.state = st <= limit;
-  L.total = L.state ? st : off;
+  L.topo = off <= limit;
+  if (L.topo) L.total = off;
+  L.rec = off; off += blk_align((size_t)N * sizeof(BeadRec));
+  L.cal = off; off += blk_align((size_t)cal_stride * sizeof(CalEnt));
+  L.er34 = off; off += blk_align((size_t)N * 8);
+  L.state = L.topo && off <= limit;
+  if (L.state) L.total = off;
   return L;
 }
 
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(BK_MAXW * 32, 1) dmd_block_loop_kernel(DevArra
     int32_t* const ger34 = r.er34;
     uint16_t* const gnup = r.nup;
     uint16_t* const gndn = r.ndn;
-    {  // topology words and list lengths are always resident
+    if (L.topo) {  // topology words and list lengths
       uint32_t* smeta = reinterpret_cast<uint32_t*>(blk_smem + L.meta);
       uint16_t* snup = reinterpret_cast<uint16_t*>(blk_smem + L.nup);
       uint16_t* sndn = reinterpret_cast<uint16_t*>(blk_smem + L.ndn);
@@ -179,13 +182,15 @@ __global__ void __launch_bounds__(BK_MAXW * 32, 1) dmd_block_loop_kernel(DevArra
       blk_atomic_add64(&S.n_nbr_visits, r.n_nbr_visits);
     }
     __syncthreads();
-    for (int k = tid; k < N; k += nt) {  // list lengths may have changed (rebuilds)
-      gnup[k] = r.nup[k];
-      gndn[k] = r.ndn[k];
+    if (L.topo) {
+      for (int k = tid; k < N; k += nt) {  // list lengths may have changed (rebuilds)
+        gnup[k] = r.nup[k];
+        gndn[k] = r.ndn[k];
+      }
+      r.nup = gnup;
+      r.ndn = gndn;
+      r.c.meta = d.meta;
     }
-    r.nup = gnup;
-    r.ndn = gndn;
-    r.c.meta = d.meta;
     if (L.state) {
       uint4* g4 = reinterpret_cast<uint4*>(grec);
       const uint4* srec = reinterpret_cast<const uint4*>(blk_smem + L.rec);
