@@ -143,14 +143,17 @@ def extras(tab, topo_b, sv_b, peak):
             out["single_trajectory_config2_" + name]["events_committed_per_round"] = (bs["executed"] - bs["rolled_back"]) / max(bs["rounds"], 1)
         d.close()
     topo4, sv4 = genconfig.generate_box(["KLVFFAEKLVFFAEKL"], [192], 200.0, 0.3, tab, seed=3)
-    d = DMD(tables.make_params(boxl=200.0, tstar=0.3, canon=True, n_replicas=1, engine=2), topo4, tab)
-    d.set_state(sv4)
-    d.run(5000)
-    st = d.run(50000)
-    bs = d.batch_stats()
-    out["config4_12288_beads_one_trajectory"] = {"events_per_s": 50000 / (st.device_ms * 1e-3),
-                                                 "events_committed_per_round": (bs["executed"] - bs["rolled_back"]) / max(bs["rounds"], 1)}
-    d.close()
+    for name, eng in (("cta_per_replica", 2), ("whole_gpu", 3)):
+        d = DMD(tables.make_params(boxl=200.0, tstar=0.3, canon=True, n_replicas=1, engine=eng), topo4, tab)
+        d.set_state(sv4)
+        d.run(5000)
+        t0 = time.perf_counter()
+        d.run(100000)
+        dt = time.perf_counter() - t0
+        bs = d.batch_stats()
+        out["config4_12288_beads_one_trajectory_" + name] = {
+            "events_per_s": 100000 / dt, "events_committed_per_round": (bs["executed"] - bs["rolled_back"]) / max(bs["rounds"], 1)}
+        d.close()
     nch = 35715
     boxl = BOXL * (nch / 48.0) ** (1.0 / 3.0)
     topo5, sv5 = genconfig.generate_box(["KLVFFAE"], [nch], boxl, 0.5, tab, seed=5)
@@ -167,6 +170,19 @@ def extras(tab, topo_b, sv_b, peak):
         t = min(ms[1:])
         res[name] = {"device_ms": t, "algorithmic_GB_per_s": nbytes / (t * 1e-3) / 1e9, "frac_of_measured_hbm": nbytes / (t * 1e-3) / 1e9 / peak}
     out["config5_bulk_kernels"] = res
+    d.close()
+    # the same box through the event loop: engine 3, every round of the batched commit spread over the whole GPU
+    d = DMD(tables.make_params(boxl=boxl, tstar=0.5, canon=True, n_replicas=1, engine=3, nbr_capacity=32), topo5, tab)
+    d.set_state(sv5)
+    d.run(200000)
+    b0 = d.batch_stats()
+    t0 = time.perf_counter()
+    d.run(2000000)
+    dt = time.perf_counter() - t0
+    b1 = d.batch_stats()
+    out["config5_1e6_beads_one_trajectory_whole_gpu_engine"] = {
+        "events_per_s": 2000000 / dt, "timing": "wall clock around dmdb_run (kernel relaunches at pseudo-events included)",
+        "events_committed_per_round": (b1["executed"] - b1["rolled_back"] - b0["executed"] + b0["rolled_back"]) / max(b1["rounds"] - b0["rounds"], 1)}
     d.close()
     return out
 

@@ -82,7 +82,8 @@ typedef struct dmdb_params {
   int32_t log_capacity; /* per-replica event-log ring capacity in events (0 = no log) */
   int32_t engine;       /* event-loop engine: 0 = automatic, 1 = one warp per replica (throughput: thousands of
                            replicas), 2 = one CTA per replica with batched conservative commit (latency: a few
-                           trajectories; state resident in shared memory).  Results are bit-identical. */
+                           trajectories; state resident in shared memory), 3 = the same batched commit with every round spread
+                           over the whole GPU (one large system, e.g. 10^6 beads).  Results are bit-identical. */
   uint64_t seed;        /* replica r draws from the counter RNG stream seed + r (replaces Intel drandm) */
 } dmdb_params;
 

@@ -241,8 +241,8 @@ DMD_DEV void blk_phase_claim(BlkShared& S, const Rep& r, uint32_t* claim, int w,
 }
 
 // ---- check: do I hold every stamp?
-DMD_DEV void blk_phase_check(BlkShared& S, const Rep& r, const uint32_t* claim, int w, const ListRef& li,
-                             const ListRef& lj) {
+template <class SH>
+DMD_DEV void blk_phase_check(SH& S, const Rep& r, const uint32_t* claim, int w, const ListRef& li, const ListRef& lj) {
   const BlkSlot& sl = S.slot[w];
   int bad = 0;
   blk_footprint(r, sl.owner, sl.j, li, lj, [&](int b) {
@@ -260,7 +260,8 @@ DMD_DEV int blk_n_exec(const BlkShared& S, int batch) {  // redundant per warp: 
 }
 
 // ---- exec: one hot pair event (main.F90:1636 eventdyn + :943 partial_events) with undo logging
-DMD_DEV void blk_exec_event(BlkShared& S, Rep& r, int w, const ListRef& li, const ListRef& lj) {
+template <class SH>
+DMD_DEV void blk_exec_event(SH& S, Rep& r, int w, const ListRef& li, const ListRef& lj) {
   BlkSlot& sl = S.slot[w];
   const int i = sl.owner;
   const CalEnt ev = r.cal[i];
@@ -298,7 +299,8 @@ DMD_DEV void blk_exec_event(BlkShared& S, Rep& r, int w, const ListRef& li, cons
   }
 }
 
-DMD_DEV void blk_rollback(BlkShared& S, Rep& r, int w) {
+template <class SH>
+DMD_DEV void blk_rollback(SH& S, Rep& r, int w) {
   if (Warp::lane() == 0) {
     const BlkSlot& sl = S.slot[w];
     for (int q = sl.n_undo - 1; q >= 0; q--) r.cal[S.undo_idx[w][q]] = S.undo_old[w][q];

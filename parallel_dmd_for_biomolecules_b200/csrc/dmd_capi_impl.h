@@ -17,7 +17,7 @@
 #include "dmd_types.h"
 
 namespace dmd {
-enum Op { OP_START = 0, OP_NBOR, OP_PREDICT_ALL, OP_RUN, OP_SYNC_POS, OP_ENERGY, OP_EVCODE, OP_RETEMP, OP_RUN_BLOCK };
+enum Op { OP_START = 0, OP_NBOR, OP_PREDICT_ALL, OP_RUN, OP_SYNC_POS, OP_ENERGY, OP_EVCODE, OP_RETEMP, OP_RUN_BLOCK, OP_RUN_GRID };
 }
 
 static thread_local std::string g_create_error;
@@ -109,7 +109,7 @@ extern "C" {
 int dmdb_create(const dmdb_params* p, const dmdb_topology* topo, const dmdb_tables* tab, dmdb_handle** out) {
   if (!p || !topo || !tab || !out) return fail(nullptr, DMDB_ERR_ARG, "null argument");
   if (p->n_replicas < 1) return fail(nullptr, DMDB_ERR_ARG, "n_replicas must be >= 1");
-  if (p->engine < 0 || p->engine > 2) return fail(nullptr, DMDB_ERR_ARG, "engine must be 0 (auto), 1 (warp) or 2 (block)");
+  if (p->engine < 0 || p->engine > 3) return fail(nullptr, DMDB_ERR_ARG, "engine must be 0 (auto), 1 (warp), 2 (block) or 3 (grid)");
   std::string err;
   if (!be::init(p->device, err)) return fail(nullptr, DMDB_ERR_NO_DEVICE, err);
   std::unique_ptr<dmdb_handle> h(new dmdb_handle());
@@ -300,10 +300,12 @@ static int run_impl(dmdb_handle* h, int64_t n_events, dmdb_stats* stats, int fla
   // engine choice: one warp per replica fills the GPU from ~1000 replicas on; below that the CTA-per-replica
   // engine (batched conservative commit, state in shared memory) is an order of magnitude faster per trajectory
   int engine = h->model.params.engine;
-  if (engine == 0) engine = h->d.n_replicas >= 1184 ? 1 : 2;
+  // a large single system gets the whole GPU per round (engine 3)
+  if (engine == 0) engine = h->d.n_replicas >= 1184 ? 1 : ((h->d.n_replicas <= 2 && h->model.sys.N >= 100000 && !flags) ? 3 : 2);
+  if (engine == 3 && (flags || !be::grid_engine_available())) engine = 2;  // (run_until_output: engines 1 and 2)
   if (engine == 2 && !be::block_engine_fits(h->model.sys)) engine = 1;
-  DMDB_TRY(h, be::run_op(h->d, engine == 2 ? dmd::OP_RUN_BLOCK : dmd::OP_RUN, 0, h->d.n_replicas, n_events, nullptr,
-                         nullptr, &h->last_ms, &h->last_launches, flags);)
+  const int op = engine == 3 ? dmd::OP_RUN_GRID : (engine == 2 ? dmd::OP_RUN_BLOCK : dmd::OP_RUN);
+  DMDB_TRY(h, be::run_op(h->d, op, 0, h->d.n_replicas, n_events, nullptr, nullptr, &h->last_ms, &h->last_launches, flags);)
   rc = check_device_errors(h);
   if (rc) return rc;
   if (stats) return dmdb_get_replica_stats(h, -1, stats);

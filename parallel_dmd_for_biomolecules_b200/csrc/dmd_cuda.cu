@@ -4,6 +4,7 @@
 //   dmd_event_loop_kernel    the persistent event loop, main.F90:484-1258 (dmdb_run, engine 1: warp per replica)
 //   dmd_block_loop_kernel    the same loop with one CTA per replica, state in shared memory, batched
 //                            conservative commit of independent events (dmdb_run, engine 2; dmd_block.h)
+//   dmd_grid_loop_kernel     the same rounds spread over every SM for ONE large system (dmdb_run, engine 3; dmd_grid.h)
 //   dmd_bulk_*_kernel        grid-parallel, one thread per bead, any system size: run start (init, fix-up of
 //                            main.F90:249-321 through the cell grid), cell_add.f, nbor.f, events.f, group minima
 //                            (dmdb_set_state*, dmdb_nbor, dmdb_predict_all)
@@ -14,11 +15,17 @@
 // There is no CPU fallback: be::init fails when no CUDA device is present.
 #include <cuda_runtime.h>
 
+#include <chrono>
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 
 #include "dmd_block.h"
 #include "dmd_engine.h"
+#include "dmd_grid.h"
 #include "dmd_types.h"
 
 #define CUDA_OK(x)                                                                                   \
@@ -35,6 +42,7 @@ namespace dmd {
                     // the loop is bound by dependent latencies, so resident warps beat the extra spills
 #endif
 constexpr int WARPS_PER_CTA = DMD_WPC;
+constexpr int BULK_THREADS = 256;  // CTA size of the thread-per-bead bulk kernels
 #ifndef DMD_MIN_CTAS
 #define DMD_MIN_CTAS 1
 #endif
@@ -226,6 +234,120 @@ __global__ void __launch_bounds__(BK_MAXW * 32, 1) dmd_block_loop_kernel(DevArra
   }
 }
 
+// ---- the interval pseudo-event (main.F90:1126-1187, interval_event_cold in dmd_engine.h) for a large system,
+// spread over the grid: begin (one thread: event time -> scalars), advance (thread per bead: shift the calendar,
+// move the beads, largest displacement), decide (one thread: displ.f:37-46, main.F90:1150-1157), and -- when the
+// lists have to be rebuilt -- wrap + the bulk cell / nbor / predict kernels.  Same arithmetic as the serial code.
+__global__ void dmd_interval_begin_kernel(DevArrays d, int rid) {
+  Rep r;
+  rep_bind(r, d, staged_global(d), nullptr, rid);
+  RepScalars& q = *r.sc;
+  const double tf = r.cal[r.N + 1].t;
+  q.tfalse = tf;            // main.F90:639-643
+  q.coll = q.coll + 1;
+  q.t = q.t + tf;           // :1129
+  q.interval_max = q.interval_max - tf;
+  *reinterpret_cast<unsigned long long*>(&q.pad[2]) = 0ull;  // largest displacement (bits of a non-negative double)
+}
+__global__ void __launch_bounds__(BULK_THREADS) dmd_interval_advance_kernel(DevArrays d, int rid) {
+  Rep r;
+  rep_bind(r, d, staged_global(d), nullptr, rid);
+  const int k = blockIdx.x * BULK_THREADS + threadIdx.x;
+  const double tf = r.tfalse;
+  if (k < r.N + 3) r.cal[k].t = r.cal[k].t - tf;  // :1133-1135
+  double moved = 0.0;
+  if (k < r.N) {  // :1140-1144 + displ.f:20-33
+    BeadRec* p = &r.rec[k];
+    double x = p->x + p->vx * tf, y = p->y + p->vy * tf, z = p->z + p->vz * tf;
+    p->x = x; p->y = y; p->z = z;
+    double a = r.oldr[3 * k] - x, b = r.oldr[3 * k + 1] - y, cc = r.oldr[3 * k + 2] - z;
+    double dis = a * a + b * b + cc * cc;
+    moved = dis / r.c.sys->hdelr;
+  }
+  moved = warp_max(moved);
+  if (Warp::lane() == 0 && moved > 0.0)
+    atomicMax(reinterpret_cast<unsigned long long*>(&r.sc->pad[2]), (unsigned long long)__double_as_longlong(moved));
+}
+__global__ void dmd_interval_decide_kernel(DevArrays d, int rid) {
+  Rep r;
+  rep_bind(r, d, staged_global(d), nullptr, rid);
+  const double moved_far = __longlong_as_double((long long)*reinterpret_cast<unsigned long long*>(&r.sc->pad[2]));
+  r.tfalse = 0.0;
+  bool update = false;
+  if (moved_far >= 0.1) {  // displ.f:37-46
+    update = true;
+    if (moved_far >= 1.25 * 1.25) {
+      r.t_fact = r.t_fact / 1.01;
+      r.interval = r.t_fact / dmd_sqrt(r.setemp);
+    }
+  }
+  const bool rebuild = update || r.interval > r.interval_max;  // :1150-1179
+  if (rebuild) {
+    if (!update) {
+      r.sc->nforcedupdate += 1;
+      r.n_forced = r.n_forced * 1.01;
+    }
+    r.interval_max = r.interval * r.n_forced;
+    r.sc->nupdates += 1;
+  }
+  r.cal[r.N + 1].t = r.interval * 0.999;  // :1181 (the bulk prediction only writes bead entries)
+  r.old_tfalse = 0.0;
+  if (r.n_log < r.c.sys->log_cap) {
+    EventLogRec e;
+    e.t = r.t;
+    e.i = r.N + 2;
+    e.j = 0;
+    e.type = -2;
+    e.evcode = 0;
+    r.log[r.n_log] = e;
+    r.n_log++;
+  }
+  RepScalars& q = *r.sc;  // (one thread: store the scalars directly)
+  q.tfalse = r.tfalse; q.old_tfalse = r.old_tfalse; q.interval = r.interval; q.t_fact = r.t_fact;
+  q.interval_max = r.interval_max; q.n_forced = r.n_forced; q.n_log = r.n_log;
+  q.pad[1] = rebuild ? 1 : 0;
+}
+__global__ void __launch_bounds__(BULK_THREADS) dmd_interval_wrap_kernel(DevArrays d, int rid) {
+  Rep r;
+  rep_bind(r, d, staged_global(d), nullptr, rid);
+  const int k = blockIdx.x * BULK_THREADS + threadIdx.x;
+  if (k >= r.N) return;
+  BeadRec* p = &r.rec[k];
+  double x = p->x - dmd_round(p->x), y = p->y - dmd_round(p->y), z = p->z - dmd_round(p->z);
+  p->x = x; p->y = y; p->z = z;
+  r.oldr[3 * k] = x; r.oldr[3 * k + 1] = y; r.oldr[3 * k + 2] = z;
+}
+
+// ---- whole-GPU engine for one large system (dmd_grid.h): cooperative launch, one CTA per SM
+__global__ void __launch_bounds__(BK_MAXW * 32, 1) dmd_grid_loop_kernel(DevArrays d, int rid, GridShared* S, uint32_t* claim) {
+  __shared__ SmemConsts sconst;
+  __shared__ int32_t s_cq[BK_MAXW][CQ_CAP];
+  const Staged tab = stage_consts(d, &sconst);
+  const int w = threadIdx.x >> 5;
+  const int gw = blockIdx.x * BK_MAXW + w, ngw = gridDim.x * BK_MAXW;
+  Rep r;
+  rep_bind(r, d, tab, s_cq[w], rid);
+  const int64_t pp0 = r.n_pair_pred, nv0 = r.n_nbr_visits;
+  if (gw == 0) r.n_log = S->n_log;
+  grid_run(*S, r, claim, gw, ngw);
+  if (Warp::lane() == 0 && gw != 0) {  // work counters of the other warps
+    atomicAdd((unsigned long long*)&S->nevents[30], (unsigned long long)(r.n_pair_pred - pp0));
+    atomicAdd((unsigned long long*)&S->nevents[31], (unsigned long long)(r.n_nbr_visits - nv0));
+  }
+  if (gw == 0) {
+    if (S->error && !r.error) {
+      r.error = S->error;
+      r.error_info = S->error_info;
+    }
+    rep_save(r);
+    if (Warp::lane() == 0) {
+      for (int q = 0; q < 30; q++) r.sc->nevents[q] += S->nevents[q];
+      long long* st = d.blkstat + (size_t)rid * 16;
+      st[0] += S->st_rounds; st[1] += S->st_exec; st[2] += S->st_rollback; st[3] += S->st_conflict;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_sync_positions_kernel(DevArrays d, int r0, int nrep) {
   int rid = replica_of_warp(r0, nrep);
   if (rid < 0) return;
@@ -262,7 +384,6 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_retemp_kernel(DevArray
 // ---- grid-parallel bulk kernels: ONE THREAD PER BEAD, blockIdx.y = replica.  Any system size and replica count
 // (a 10^6-bead box is one replica spread over the whole GPU; 2368 small replicas are 2368 rows of CTAs).
 // They read the tables through global memory (L1/L2 resident) instead of staging 31 KB per small CTA.
-constexpr int BULK_THREADS = 256;
 __device__ __forceinline__ bool bulk_bind(Rep& r, const DevArrays& d, int r0, int& k) {
   rep_bind(r, d, staged_global(d), nullptr, r0 + blockIdx.y);
   k = blockIdx.x * BULK_THREADS + threadIdx.x;
@@ -508,6 +629,108 @@ inline void run_pack(const dmd::DevArrays& d, double* sv, int32_t* bp) {
   CUDA_OK(cudaGetLastError());
 }
 
+inline bool grid_engine_available() { return true; }
+// engine 3: one large system on the whole GPU.  The grid kernel commits batches of plain pair events until the head
+// of the calendar is something else (ghost, interval, output, H-bond event); that one entry is processed by the
+// warp-per-replica engine (after refreshing its group minima) and the grid kernel is relaunched.
+static dmd::GridShared* g_grid = nullptr;
+static uint32_t* g_grid_claim = nullptr;
+static size_t g_grid_claim_n = 0;
+inline int run_grid(const dmd::DevArrays& d, int r0, int nrep, long long n_events) {
+  using namespace dmd;
+  int dev = 0, sms = 0, coop = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  if (!coop) throw std::runtime_error("device does not support cooperative launch");
+  if (!g_grid) g_grid = (GridShared*)alloc(sizeof(GridShared));
+  const size_t nclaim = (size_t)d.n_beads + 3;
+  if (g_grid_claim_n < nclaim) {
+    if (g_grid_claim) release(g_grid_claim);
+    g_grid_claim = (uint32_t*)alloc(nclaim * 4);
+    g_grid_claim_n = nclaim;
+  }
+  CUDA_OK(cudaMemsetAsync(g_grid_claim, 0xff, nclaim * 4, g_stream));
+  if (sms * BK_MAXW > GW) sms = GW / BK_MAXW;
+  int launches = 0;
+  const size_t header = offsetof(GridShared, cand_t);
+  for (int rid = r0; rid < r0 + nrep; rid++) {
+    RepScalars sc;
+    d2h(&sc, d.scal + rid, sizeof(sc));
+    if (sc.error) continue;
+    const long long target = sc.coll + n_events;
+    static GridShared hdr;  // only its header part is used on the host
+    std::memset(&hdr, 0, header);
+    hdr.window = sc.interval * 0.02;
+    while (sc.coll < target && !sc.error) {
+      hdr.tlast = -1.0;
+      hdr.coll = sc.coll;
+      hdr.target = target;
+      hdr.tmin_bits = ~0ull;
+      hdr.barrier = 0;
+      hdr.n_cand = 0;
+      hdr.first_cold = 0x7fffffff;
+      hdr.first_lost = 0x7fffffff;
+      hdr.status = 0;
+      hdr.error = 0;
+      hdr.n_log = sc.n_log;
+      hdr.st_rounds = hdr.st_exec = hdr.st_rollback = hdr.st_conflict = 0;
+      std::memset(hdr.nevents, 0, sizeof(hdr.nevents));
+      CUDA_OK(cudaMemcpyAsync(g_grid, &hdr, header, cudaMemcpyHostToDevice, g_stream));
+      DevArrays dd = d;
+      GridShared* S = g_grid;
+      uint32_t* claim = g_grid_claim;
+      void* args[] = {&dd, &rid, &S, &claim};
+      const auto tk0 = std::chrono::steady_clock::now();
+      CUDA_OK(cudaLaunchCooperativeKernel((void*)dmd_grid_loop_kernel, dim3(sms), dim3(BK_MAXW * 32), args, 0, g_stream));
+      launches++;
+      CUDA_OK(cudaMemcpyAsync(&hdr, g_grid, header, cudaMemcpyDeviceToHost, g_stream));
+      CUDA_OK(cudaStreamSynchronize(g_stream));
+      if (getenv("DMDB_DEBUG")) {
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tk0).count();
+        fprintf(stderr, "grid launch: %.3f ms, status %d, coll %lld, rounds %lld\n", ms, hdr.status, hdr.coll, hdr.st_rounds);
+      }
+      d2h(&sc, d.scal + rid, sizeof(sc));
+      if (hdr.nevents[30] || hdr.nevents[31]) {  // work counters of the warps other than the master
+        sc.n_pair_pred += hdr.nevents[30];
+        sc.n_nbr_visits += hdr.nevents[31];
+        h2d(d.scal + rid, &sc, sizeof(sc));
+      }
+      if (hdr.status == 1 && !sc.error && sc.coll < target && hdr.head_owner == d.n_beads + 1) {
+        // the interval pseudo-event, grid-wide
+        const dim3 gb = bulk_grid(d, 1, d.n_beads + 3);
+        dmd_interval_begin_kernel<<<1, 1, 0, g_stream>>>(d, rid);
+        dmd_interval_advance_kernel<<<gb.x, BULK_THREADS, 0, g_stream>>>(d, rid);
+        dmd_interval_decide_kernel<<<1, 1, 0, g_stream>>>(d, rid);
+        launches += 3;
+        CUDA_OK(cudaGetLastError());
+        d2h(&sc, d.scal + rid, sizeof(sc));
+        if (sc.pad[1]) {  // lists + calendar rebuilt
+          dmd_interval_wrap_kernel<<<gb.x, BULK_THREADS, 0, g_stream>>>(d, rid);
+          launch_nbor(d, rid, 1);
+          dmd_bulk_predict_kernel<<<bulk_grid(d, 1, d.n_beads), BULK_THREADS, 0, g_stream>>>(d, rid);
+          launches += 5;
+          CUDA_OK(cudaGetLastError());
+          d2h(&sc, d.scal + rid, sizeof(sc));
+        }
+      } else if (hdr.status == 1 && !sc.error && sc.coll < target) {  // one calendar entry for the serial engine
+        dmd_bulk_groups_kernel<<<dim3((d.cal_stride / 32 + BULK_THREADS / 32 - 1) / (BULK_THREADS / 32), 1), BULK_THREADS, 0, g_stream>>>(d, rid);
+        const auto tc0 = std::chrono::steady_clock::now();
+        dmd_event_loop_kernel<<<1, WARPS_PER_CTA * 32, 0, g_stream>>>(d, rid, 1, 1, 0);
+        launches += 2;
+        CUDA_OK(cudaGetLastError());
+        d2h(&sc, d.scal + rid, sizeof(sc));
+        if (getenv("DMDB_DEBUG"))
+          fprintf(stderr, "cold event: %.3f ms\n",
+                  std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count());
+      } else if (hdr.status == 2) {
+        break;
+      }
+    }
+  }
+  return launches;
+}
+
 // one launcher per device operation; times the kernel with CUDA events on the launching stream
 inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long arg, int32_t* ibuf, dmd::OutRec* eout,
                    double* ms, int* launches, int flags = 0) {
@@ -536,6 +759,7 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
       dmd_block_loop_kernel<<<g, BK_MAXW * 32, L.total, g_stream>>>(d, r0, nrep, arg, (unsigned)smem_optin(), flags);
       break;
     }
+    case 9: nl = run_grid(d, r0, nrep, arg); break;
     default: throw std::runtime_error("unknown device op");
   }
   CUDA_OK(cudaGetLastError());

@@ -200,7 +200,7 @@ def test_errors_are_reported_not_fatal(tab, system_b):
         dev2.set_state(sv[:10])
 
 
-@pytest.mark.parametrize("engine", [1, 2])
+@pytest.mark.parametrize("engine", [1, 2, 3])
 def test_config4_12288_beads_matches_oracle(tab, engine):
     """BASELINE config 4 (192 chains x 16 residues = 12 288 beads): too large for the shared-memory state of the
     CTA-per-replica engine, which then works on the global arrays; cells, lists, calendar and 20 000 committed events
@@ -210,7 +210,7 @@ def test_config4_12288_beads_matches_oracle(tab, engine):
     p = tables.make_params(boxl=200.0, tstar=0.3, canon=True, n_replicas=2, log_capacity=20000, engine=engine)
     ora, dev = _pair(p, topo, tab, sv)
     compare_engines(ora, dev, n_events=20000)
-    if engine == 2:
+    if engine >= 2:
         st = dev.batch_stats(0)
         assert (st["executed"] - st["rolled_back"]) / st["rounds"] > 8.0  # larger box, larger batches
 
@@ -257,3 +257,35 @@ def test_config5_million_bead_box_bulk_kernels(tab):
     dev.events()
     tim2, nptnr2, coltype2 = dev.calendar(0)
     assert np.array_equal(tim, tim2) and np.array_equal(nptnr, nptnr2) and np.array_equal(coltype, coltype2)
+
+
+def test_whole_gpu_engine_on_small_and_million_bead_boxes(tab, system_b):
+    """Engine 3 (every round of the batched commit spread over the whole GPU; interval events through the bulk
+    kernels): the oracle's sequence on config 2 (thermostat, interval events, list rebuilds on the way), and on the
+    1 000 020-bead box of config 5 -- where the oracle cannot start -- exact NVE energy conservation over 10^6
+    events with hundreds of events committed per round, and no overlap / broken bond in a sampled region."""
+    topo, sv, boxl = system_b
+    n = 60000
+    p = tables.make_params(boxl=boxl, tstar=0.18, canon=True, n_replicas=1, log_capacity=n, engine=3)
+    ora, dev = _pair(p, topo, tab, sv)
+    compare_engines(ora, dev, n_events=n)
+    assert dev.stats(0).updates + dev.stats(0).forced_updates > 10  # list rebuilds happened
+    nch = 35715
+    boxl5 = 158.54 * (nch / 48.0) ** (1.0 / 3.0)
+    topo5, sv5 = genconfig.generate_box(["KLVFFAE"], [nch], boxl5, 0.5, tab, seed=5)
+    d = DMD(tables.make_params(boxl=boxl5, tstar=0.5, canon=False, n_replicas=1, engine=3, nbr_capacity=32), topo5, tab)
+    d.set_state(sv5)
+    e0 = d.energy(0)
+    st = d.run(1000000)
+    e1 = d.energy(0)
+    assert st.events == 1000000
+    assert abs(e1.ered - e0.ered) < 1e-6 * abs(e0.ered) and abs(e1.ered - e0.ered) < 1e-3
+    bs = d.batch_stats(0)
+    assert (bs["executed"] - bs["rolled_back"]) / bs["rounds"] > 100
+    # bonds of the first chains are still inside their windows (positions brought to the current time)
+    d.sync_positions()
+    x = d.state(0)["sv"][:28 * 50, :3].reshape(50, 28, 3)
+    dca = x[:, 1:7] - x[:, 0:6]
+    dca -= np.round(dca)
+    dist = np.sqrt((dca ** 2).sum(-1)) * boxl5
+    assert np.all(np.abs(dist - 3.8) <= 3.8 * 0.02375 + 1e-9)  # Ca-Ca pseudo-bond window (def.h:10,39)
