@@ -300,8 +300,9 @@ static int run_impl(dmdb_handle* h, int64_t n_events, dmdb_stats* stats, int fla
   // engine choice: one warp per replica fills the GPU from ~1000 replicas on; below that the CTA-per-replica
   // engine (batched conservative commit, state in shared memory) is an order of magnitude faster per trajectory
   int engine = h->model.params.engine;
-  // a large single system gets the whole GPU per round (engine 3)
-  if (engine == 0) engine = h->d.n_replicas >= 1184 ? 1 : ((h->d.n_replicas <= 2 && h->model.sys.N >= 100000 && !flags) ? 3 : 2);
+  // a single system of >= 8192 beads gets the whole GPU per round (engine 3): measured 8.0e5 vs 5.1e5 events/s at
+  // 12 288 beads, 5.5e6 at 10^6 beads; below that its kernel relaunches at pseudo-events cost more than it gains
+  if (engine == 0) engine = h->d.n_replicas >= 1184 ? 1 : ((h->d.n_replicas == 1 && h->model.sys.N >= 8192 && !flags) ? 3 : 2);
   if (engine == 3 && (flags || !be::grid_engine_available())) engine = 2;  // (run_until_output: engines 1 and 2)
   if (engine == 2 && !be::block_engine_fits(h->model.sys)) engine = 1;
   const int op = engine == 3 ? dmd::OP_RUN_GRID : (engine == 2 ? dmd::OP_RUN_BLOCK : dmd::OP_RUN);
