@@ -289,3 +289,34 @@ def test_whole_gpu_engine_on_small_and_million_bead_boxes(tab, system_b):
     dca -= np.round(dca)
     dist = np.sqrt((dca ** 2).sum(-1)) * boxl5
     assert np.all(np.abs(dist - 3.8) <= 3.8 * 0.02375 + 1e-9)  # Ca-Ca pseudo-bond window (def.h:10,39)
+
+
+def test_long_run_statistics_match_the_oracle_ensemble(tab):
+    """North-star 'longer runs': an H-bond forming box (8 x A12, T* = 0.10) run for 1.5e6 events.  Beyond the
+    bit-identical replica (same seed), an ensemble of 64 device replicas with OTHER seeds is statistically
+    indistinguishable from an ensemble of 6 oracle trajectories: thermostat temperature, potential energy and
+    H-bond count agree within the ensembles' standard errors."""
+    topo, sv = genconfig.generate_box(["AAAAAAAAAAAA"], [8], 45.0, 0.10, tab, seed=1)
+    n = 1500000
+    R = 64
+    dev = DMD(tables.make_params(boxl=45.0, tstar=0.10, canon=True, n_replicas=R, seed=1000, engine=1), topo, tab)
+    dev.set_state(sv)
+    dev.run(n)
+    ep_d, _ = dev.potential_energies()
+    hb_d = np.array([dev.energy(r).hb_ii + dev.energy(r).hb_ij for r in range(R)])
+    t_d = np.array([dev.energy(r).tred for r in range(R)])
+    ep_o, hb_o, t_o = [], [], []
+    for seed in range(6):
+        o = OracleDMD(tables.make_params(boxl=45.0, tstar=0.10, canon=True, seed=seed + 1), topo, tab)
+        o.set_state(sv)
+        o.run(n)
+        e = o.energy()
+        ep_o.append(e.ered - 0.5 * e.sumvel)
+        hb_o.append(e.hb_ii + e.hb_ij)
+        t_o.append(e.tred)
+    ep_o, hb_o, t_o = np.array(ep_o), np.array(hb_o), np.array(t_o)
+    assert abs(t_d.mean() - 1.2) < 0.03 and abs(t_o.mean() - 1.2) < 0.08  # setemp = 12 T*
+    for a, b in ((ep_d, ep_o), (hb_d.astype(float), hb_o.astype(float))):
+        se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
+        assert abs(a.mean() - b.mean()) < 4.0 * se + 1e-9, (a.mean(), b.mean(), se)
+    assert hb_d.mean() > 1.0  # hydrogen bonds did form

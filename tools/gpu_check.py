@@ -66,7 +66,7 @@ def main():
             print(" replica 1 differs from replica 0 (different RNG stream):", not np.array_equal(lc["i"][:5000], lb["i"][:5000]))
         d.close()
     # ---- throughput sweep
-    for R in (148, 592, 1184, 2368, 4736):
+    for R in (148, 592, 1184, 4144, 8288):
         p = tables.make_params(boxl=110.0, tstar=0.5, canon=True, n_replicas=R, log_capacity=0)
         d = DMD(p, topo, tab)
         t0 = time.time()
