@@ -344,6 +344,7 @@ __global__ void __launch_bounds__(BK_MAXW * 32, 1) dmd_grid_loop_kernel(DevArray
       for (int q = 0; q < 30; q++) r.sc->nevents[q] += S->nevents[q];
       long long* st = d.blkstat + (size_t)rid * 16;
       st[0] += S->st_rounds; st[1] += S->st_exec; st[2] += S->st_rollback; st[3] += S->st_conflict;
+      st[8] += S->cyc[0]; st[9] += S->cyc[1]; st[10] += S->cyc[2]; st[11] += S->cyc[3]; st[12] += S->cyc[4]; st[13] += S->cyc[5];
     }
   }
 }
@@ -676,6 +677,7 @@ inline int run_grid(const dmd::DevArrays& d, int r0, int nrep, long long n_event
       hdr.n_log = sc.n_log;
       hdr.st_rounds = hdr.st_exec = hdr.st_rollback = hdr.st_conflict = 0;
       std::memset(hdr.nevents, 0, sizeof(hdr.nevents));
+      std::memset(hdr.cyc, 0, sizeof(hdr.cyc));
       CUDA_OK(cudaMemcpyAsync(g_grid, &hdr, header, cudaMemcpyHostToDevice, g_stream));
       DevArrays dd = d;
       GridShared* S = g_grid;

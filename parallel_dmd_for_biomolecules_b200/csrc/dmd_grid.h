@@ -25,6 +25,7 @@ struct GridShared {
   long long coll, target;
   long long st_rounds, st_exec, st_rollback, st_conflict;
   long long nevents[32];
+  long long cyc[8];              // SM clocks per phase (thread 0): scan, rank, claim, check, exec, commit
   unsigned long long tmin_bits;  // order-preserving image of the calendar minimum (atomicMin)
   unsigned barrier;              // grid barrier arrival counter
   int n_cand, first_cold, first_lost;
@@ -33,6 +34,7 @@ struct GridShared {
   int n_log;
   int head_owner;                // owner of the calendar head when status == 1
   double cand_t[GK];
+  double slot_t[GW], slot_newmin[GW];  // compact copies of slot[].t / slot[].newmin for the validation sweep
   int cand_o[GK];
   int by_rank[GK];
   BlkSlot slot[GW];
@@ -68,7 +70,10 @@ __device__ void grid_run(GridShared& S, Rep& r, uint32_t* claim, int gw, int ngw
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gnt = gridDim.x * blockDim.x;
   const bool t0 = gtid == 0;
   unsigned epoch = 0;
-  __shared__ int s_nvalid;
+  constexpr int GRID_STAGE = 256;
+  __shared__ int s_nvalid, s_ncand, s_base;
+  __shared__ double s_ct[GRID_STAGE];
+  __shared__ int s_co[GRID_STAGE];
   while (true) {
     grid_barrier(S, epoch);
     if (S.error || S.coll >= S.target) {
@@ -76,6 +81,7 @@ __device__ void grid_run(GridShared& S, Rep& r, uint32_t* claim, int gw, int ngw
       break;
     }
     const long long remaining = S.target - S.coll;
+    long long tc = clock64();
     // ---- scan + select (one sweep when the time of the last committed event is known)
     double window = S.window;
     bool known = S.tlast >= 0.0;
@@ -85,17 +91,37 @@ __device__ void grid_run(GridShared& S, Rep& r, uint32_t* claim, int gw, int ngw
     while (true) {
       const double lim = known ? S.tlast + window : (tries ? tmin + window : -1.0);
       double best = T_PAD;
+      if (threadIdx.x == 0) s_ncand = 0;
+      __syncthreads();
       for (int k = gtid; k < r.N + 3; k += gnt) {
         const CalEnt e = r.cal[k];
         if (e.t < best) best = e.t;
-        if (e.t <= lim) {
-          const int pos = atomicAdd(&S.n_cand, 1);
-          if (pos < GK) {
-            const int ct = type_of(e.type);
-            S.cand_t[pos] = e.t;
-            S.cand_o[pos] = (k < r.N && e.ptnr >= 0 && ct >= 1 && ct <= 3) ? k : -1 - k;  // negative: not a hot event
+        if (e.t <= lim) {  // candidates are staged per CTA: one global reservation per CTA instead of one per candidate
+          const int ct = type_of(e.type);
+          const int code = (k < r.N && e.ptnr >= 0 && ct >= 1 && ct <= 3) ? k : -1 - k;  // negative: not a hot event
+          const int pos = atomicAdd(&s_ncand, 1);
+          if (pos < GRID_STAGE) {
+            s_ct[pos] = e.t;
+            s_co[pos] = code;
+          } else {  // (a very dense window: straight to the global list)
+            const int gp = atomicAdd(&S.n_cand, 1);
+            if (gp < GK) {
+              S.cand_t[gp] = e.t;
+              S.cand_o[gp] = code;
+            }
           }
         }
+      }
+      __syncthreads();
+      {
+        const int ns = s_ncand < GRID_STAGE ? s_ncand : GRID_STAGE;
+        if (threadIdx.x == 0) s_base = ns ? atomicAdd(&S.n_cand, ns) : 0;
+        __syncthreads();
+        for (int q = threadIdx.x; q < ns; q += blockDim.x)
+          if (s_base + q < GK) {
+            S.cand_t[s_base + q] = s_ct[q];
+            S.cand_o[s_base + q] = s_co[q];
+          }
       }
       best = warp_min(best);
       if (Warp::lane() == 0) atomicMin(&S.tmin_bits, ord_bits(best));
@@ -121,6 +147,7 @@ __device__ void grid_run(GridShared& S, Rep& r, uint32_t* claim, int gw, int ngw
       }
       continue;
     }
+    if (t0) S.cyc[0] += clock64() - tc, tc = clock64();
     // ---- rank in serial order (time, bead index): one warp per candidate
     for (int k = gw; k < nc; k += ngw) {
       const double t = S.cand_t[k];
@@ -149,6 +176,7 @@ __device__ void grid_run(GridShared& S, Rep& r, uint32_t* claim, int gw, int ngw
       }
       break;
     }
+    if (t0) S.cyc[1] += clock64() - tc, tc = clock64();
     // ---- claim
     ListRef li, lj;
     li.up = li.dn = lj.up = lj.dn = nullptr;
@@ -170,41 +198,61 @@ __device__ void grid_run(GridShared& S, Rep& r, uint32_t* claim, int gw, int ngw
       }
     }
     grid_barrier(S, epoch);
+    if (t0) S.cyc[2] += clock64() - tc, tc = clock64();
     // ---- check
     if (gw < batch) {
       blk_phase_check(S, r, claim, gw, li, lj);
       if (Warp::lane() == 0 && !S.slot[gw].win) atomicMin(&S.first_lost, gw);
     }
     grid_barrier(S, epoch);
+    if (t0) S.cyc[3] += clock64() - tc, tc = clock64();
     // ---- exec
     const int n_exec = S.first_lost < batch ? S.first_lost : batch;  // >= 1
     if (gw < batch) {
       const BlkSlot& sl = S.slot[gw];
       blk_footprint(r, sl.owner, sl.j, li, lj, [&](int b) { claim[b] = CLAIM_FREE; });
     }
-    if (gw < n_exec) blk_exec_event(S, r, gw, li, lj);
+    if (gw < n_exec) {
+      blk_exec_event(S, r, gw, li, lj);
+      if (Warp::lane() == 0) {
+        S.slot_t[gw] = S.slot[gw].t;
+        S.slot_newmin[gw] = S.slot[gw].newmin;
+      }
+    }
     grid_barrier(S, epoch);
+    if (t0) S.cyc[4] += clock64() - tc, tc = clock64();
     // ---- validate (main.F90:970-993; warp 0 of every CTA redundantly: running prefix minimum of newmin)
     if (threadIdx.x < 32) {
       int nv = n_exec;
       double carry = T_PAD;  // minimum of newmin over all earlier slots
-      for (int base = 0; base < n_exec && nv == n_exec; base += 32) {
-        const int q = base + Warp::lane();
-        const double t = q < n_exec ? S.slot[q].t : T_PAD;
-        double pm = q < n_exec ? S.slot[q].newmin : T_PAD;
+      for (int base = 0; base < n_exec && nv == n_exec; base += 32 * 8) {
+        // eight chunks of 32 slots per trip: their loads are independent and issued together
+        double tt[8], mm[8];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const double o = Warp::shfl(pm, Warp::lane() >= d ? Warp::lane() - d : Warp::lane());
-          if (Warp::lane() >= d && o < pm) pm = o;
+        for (int c = 0; c < 8; c++) {
+          const int q = base + c * 32 + Warp::lane();
+          tt[c] = q < n_exec ? S.slot_t[q] : T_PAD;
+          mm[c] = q < n_exec ? S.slot_newmin[q] : T_PAD;
         }
-        double before = Warp::shfl(pm, Warp::lane() > 0 ? Warp::lane() - 1 : 0);
-        if (Warp::lane() == 0) before = T_PAD;
-        if (carry < before) before = carry;
-        const bool bad = q > 0 && q < n_exec && !(t < before);
-        const unsigned m = Warp::ballot(bad);
-        if (m) nv = base + dmd_ffs(m) - 1;
-        const double last = Warp::shfl(pm, 31);
-        if (last < carry) carry = last;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          if (nv != n_exec || base + c * 32 >= n_exec) break;
+          const int q = base + c * 32 + Warp::lane();
+          double pm = mm[c];
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const double o = Warp::shfl(pm, Warp::lane() >= d ? Warp::lane() - d : Warp::lane());
+            if (Warp::lane() >= d && o < pm) pm = o;
+          }
+          double before = Warp::shfl(pm, Warp::lane() > 0 ? Warp::lane() - 1 : 0);
+          if (Warp::lane() == 0) before = T_PAD;
+          if (carry < before) before = carry;
+          const bool bad = q > 0 && q < n_exec && !(tt[c] < before);
+          const unsigned m = Warp::ballot(bad);
+          if (m) nv = base + c * 32 + dmd_ffs(m) - 1;
+          const double last = Warp::shfl(pm, 31);
+          if (last < carry) carry = last;
+        }
       }
       if (Warp::lane() == 0) s_nvalid = nv;
     }
@@ -213,9 +261,12 @@ __device__ void grid_run(GridShared& S, Rep& r, uint32_t* claim, int gw, int ngw
     if (gw >= n_valid && gw < n_exec) blk_rollback(S, r, gw);
     if (gw == 0) {  // commit: tallies, log, counters (lanes over the slots)
       const int log_cap = r.c.sys->log_cap;
+      int c1 = 0, c2 = 0, c3 = 0;  // batch events are types 1, 2, 3 only
       for (int q = Warp::lane(); q < n_valid; q += 32) {
         const BlkSlot& sl = S.slot[q];
-        if (sl.ct >= 0 && sl.ct < 32) atomicAdd((unsigned long long*)&S.nevents[sl.ct], 1ull);
+        c1 += sl.ct == 1;
+        c2 += sl.ct == 2;
+        c3 += sl.ct == 3;
         if (r.n_log + q < log_cap) {
           EventLogRec e;
           e.t = r.t + sl.t;
@@ -225,6 +276,12 @@ __device__ void grid_run(GridShared& S, Rep& r, uint32_t* claim, int gw, int ngw
           e.evcode = sl.code;
           r.log[r.n_log + q] = e;
         }
+      }
+      c1 = warp_sum(c1); c2 = warp_sum(c2); c3 = warp_sum(c3);
+      if (Warp::lane() == 0) {
+        S.nevents[1] += c1;
+        S.nevents[2] += c2;
+        S.nevents[3] += c3;
       }
       if (r.n_log < log_cap) r.n_log = r.n_log + n_valid < log_cap ? r.n_log + n_valid : log_cap;
       r.coll += n_valid;
@@ -246,6 +303,7 @@ __device__ void grid_run(GridShared& S, Rep& r, uint32_t* claim, int gw, int ngw
         if (nc < want) S.window = window * 1.25;
         else if (nc > 2 * want) S.window = window * 0.8;
         else S.window = window;
+        S.cyc[5] += clock64() - tc;
       }
     }
     if (r.error && Warp::lane() == 0) {

@@ -14,3 +14,5 @@ n = int(os.environ.get("GRID_EVENTS", "400000"))
 t0 = time.time(); st = d.run(n); wall = time.time() - t0
 bs = d.batch_stats(0)
 print("N=%d: %d events in %.1f ms (%d launches) -> %.3e ev/s; rounds %d events/round %.1f" % (topo.n_beads, n, wall * 1e3, st.kernel_launches, n / wall, bs["rounds"], (bs["executed"] - bs["rolled_back"]) / max(bs["rounds"], 1)))
+r = max(bs["rounds"], 1)
+print("cycles per round (grid engine: scan, rank, claim, check, exec, commit):", [round(v / r) for v in list(bs["cycles"].values())[:6]])
