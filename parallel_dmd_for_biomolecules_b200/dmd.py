@@ -38,7 +38,7 @@ class DMDError(RuntimeError):
 
 
 def load_library(path: Optional[str] = None):
-    path = path or LIB_PATH
+    path = path or os.environ.get("DMDB_LIB") or LIB_PATH
     if not os.path.exists(path):
         raise DMDError(-1, f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(nvcc, sm_100a). There is no CPU fallback.")

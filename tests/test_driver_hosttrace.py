@@ -58,3 +58,20 @@ def test_run_until_output_stops_right_after_the_output_event(tab, hosttrace_lib)
     hundred thousand events: the run stops right after it and can go on.  (Both engines: tests/test_gpu_parity.py.)"""
     from conftest import check_run_until_output
     check_run_until_output(tab, [1], hosttrace_lib)
+
+
+def test_command_line_mirrors_dmd_stdin(monkeypatch, capsys, tab):
+    """`python -m parallel_dmd_for_biomolecules_b200 < temp_018`: T* and ncoll from stdin (main.F90:126-128, with the
+    trailing comment temp_020 carries), sizes from options instead of -D macros."""
+    import io
+    from parallel_dmd_for_biomolecules_b200 import __main__ as cli
+    seen = {}
+    monkeypatch.setattr(cli.tables, "read_parameters_dir", lambda root: tab)
+    monkeypatch.setattr(cli.tables, "read_topology_dir",
+                        lambda root, n, L, nb: tables.Topology([tables.Species.from_sequence("KLVFFAE", k) for k in n]))
+    monkeypatch.setattr(cli.driver, "run_temperature", lambda root, topo, t, tstar, ncoll, **kw: seen.update(
+        tstar=tstar, ncoll=ncoll, n=topo.n_beads, **kw) or {"run": 1})
+    monkeypatch.setattr("sys.stdin", io.StringIO("0.200D0 # temperature\n1000000000\n"))
+    assert cli.main(["--root", "/nowhere", "--nve"]) == 0
+    assert seen["tstar"] == 0.2 and seen["ncoll"] == 1000000000 and seen["n"] == 1344 and seen["canon"] is False
+    assert "noptotal 1344" in capsys.readouterr().out
