@@ -39,6 +39,31 @@ for name, (topo, sv), boxl, ts, n in cases:
         print(la[max(0, k - 3):k + 3])
         print(lb[max(0, k - 3):k + 3])
     d.close()
+if "--mid" in sys.argv:
+    # the largest box the oracle can hold (it keeps the reference's N x N ev_code matrix: 2.5 GB at 50 400 beads)
+    nch = 1800
+    boxl = 158.54 * (nch / 48.0) ** (1.0 / 3.0)
+    topo, sv = genconfig.generate_box(["KLVFFAE"], [nch], boxl, 0.5, tab, seed=9)
+    n = 100000
+    p = tables.make_params(boxl=boxl, tstar=0.5, canon=True, n_replicas=1, log_capacity=n, engine=3, nbr_capacity=32)
+    t0 = time.time()
+    o = OracleDMD(p, topo, tab)
+    o.set_state(sv)
+    t1 = time.time()
+    o.run(n)
+    t2 = time.time()
+    d = DMD(p, topo, tab)
+    d.set_state(sv)
+    t3 = time.time()
+    d.run(n)
+    t4 = time.time()
+    la, lb = o.event_log(), d.event_log(0)
+    same = all(np.array_equal(la[f], lb[f]) for f in ("i", "j", "type", "t"))
+    bs = d.batch_stats(0)
+    print("mid N=%d: sequence identical %s, sv equal %s | oracle start %.1f s, %d events %.2f s (%.3e ev/s); device %.1f ms (%.3e ev/s), events/round %.1f" % (
+        topo.n_beads, same, np.array_equal(o.state()["sv"], d.state(0)["sv"]), t1 - t0, n, t2 - t1, n / (t2 - t1), (t4 - t3) * 1e3, n / (t4 - t3),
+        (bs["executed"] - bs["rolled_back"]) / max(bs["rounds"], 1)))
+    d.close()
 if "--big" in sys.argv:
     nch = int(os.environ.get("BIG_CHAINS", "35715"))
     boxl = 158.54 * (nch / 48.0) ** (1.0 / 3.0)
