@@ -320,3 +320,17 @@ def test_long_run_statistics_match_the_oracle_ensemble(tab):
         se = np.sqrt(a.var(ddof=1) / len(a) + b.var(ddof=1) / len(b))
         assert abs(a.mean() - b.mean()) < 4.0 * se + 1e-9, (a.mean(), b.mean(), se)
     assert hb_d.mean() > 1.0  # hydrogen bonds did form
+
+
+def test_whole_gpu_engine_25200_beads_matches_oracle(tab):
+    """Engine 3 on 900 x KLVFFAE (25 200 beads, towards the largest box the oracle -- with the reference's N x N
+    ev_code matrix -- can hold): dozens of events per round, the oracle's committed sequence bit for bit."""
+    nch = 900
+    boxl = 158.54 * (nch / 48.0) ** (1.0 / 3.0)
+    topo, sv = genconfig.generate_box(["KLVFFAE"], [nch], boxl, 0.5, tab, seed=9)
+    n = 60000
+    p = tables.make_params(boxl=boxl, tstar=0.5, canon=True, n_replicas=1, log_capacity=n, engine=3, nbr_capacity=32)
+    ora, dev = _pair(p, topo, tab, sv)
+    compare_engines(ora, dev, n_events=n)
+    bs = dev.batch_stats(0)
+    assert (bs["executed"] - bs["rolled_back"]) / bs["rounds"] > 25
