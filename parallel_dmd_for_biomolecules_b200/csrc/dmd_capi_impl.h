@@ -126,6 +126,14 @@ int dmdb_create(const dmdb_params* p, const dmdb_topology* topo, const dmdb_tabl
     d.n_replicas = (int)R;
     d.cal_stride = s.ngroups * 32;
     d.n_beads = s.N;
+    d.cap = s.cap;
+    d.ngroups = s.ngroups;
+    d.log_cap = s.log_cap;
+    d.out_cap = s.out_cap;
+    {
+      const int ncc0 = (s.ncr + 1) >> 1;
+      d.ncc3 = ncc0 * ncc0 * ncc0;
+    }
     dmd::SysConst* dsys = dalloc<dmd::SysConst>(h.get(), 1);
     be::h2d(dsys, &s, sizeof(s));
     d.sys = dsys;
@@ -169,6 +177,10 @@ int dmdb_create(const dmdb_params* p, const dmdb_topology* topo, const dmdb_tabl
     d.out = dalloc<dmd::OutRec>(h.get(), R * (size_t)s.out_cap);
     d.blkstat = dalloc<long long>(h.get(), R * 16);
     be::zero(d.blkstat, R * 16 * sizeof(long long));
+    d.svc_flag = dalloc<int32_t>(h.get(), R);
+    be::zero(d.svc_flag, R * 4);
+    d.svc_ctl = dalloc<unsigned long long>(h.get(), dmd::SVC_CTL_WORDS);
+    be::zero(d.svc_ctl, dmd::SVC_CTL_WORDS * 8);
     h->eout = dalloc<dmd::OutRec>(h.get(), R);
     h->temp_buf = dalloc<double>(h.get(), R);
     be::zero(d.nup, R * N * 2);

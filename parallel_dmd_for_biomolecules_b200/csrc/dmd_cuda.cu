@@ -81,15 +81,76 @@ __device__ __forceinline__ int replica_of_warp(int r0, int nrep) {
   return w < nrep ? r0 + w : -1;
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, DMD_MIN_CTAS) dmd_event_loop_kernel(DevArrays d, int r0, int nrep, long long n_events, int flags) {
+// ---- list-rebuild service: the first n_srv CTAs of the event-loop grid serve the rebuild requests of the worker
+// warps (svc_request in dmd_engine.h) with all their threads -- cell_add.f + nbor.f + events.f for one replica at a
+// time, the same functions the CTA-per-replica engine uses -- until every worker warp has finished.
+__device__ __noinline__ void svc_serve(DevArrays d, Staged tab, int r0, int nrep) {
+  __shared__ int s_pick, s_state;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int scan0 = (int)(((long long)blockIdx.x * nrep) / (gridDim.x > 0 ? gridDim.x : 1));  // servers start at different places
+  while (true) {
+    if (tid == 0) s_pick = 0x7fffffff;
+    __syncthreads();
+    for (int k = tid; k < nrep; k += nt) {
+      int idx = k + scan0;
+      if (idx >= nrep) idx -= nrep;
+      if (*(volatile int32_t*)(d.svc_flag + r0 + idx) == 1) {
+        atomicMin(&s_pick, idx);
+        break;
+      }
+    }
+    __syncthreads();
+    const int pick = s_pick;
+    if (tid == 0) {
+      if (pick == 0x7fffffff) {
+        const unsigned long long done = *(volatile unsigned long long*)&d.svc_ctl[0];
+        s_state = done >= (unsigned long long)nrep ? 2 : 0;
+        if (s_state == 0) __nanosleep(2000);
+      } else {
+        s_state = svc_cas_acq_rel(d.svc_flag + r0 + pick, 1, 2) == 1 ? 1 : 0;
+      }
+    }
+    __syncthreads();
+    const int state = s_state;
+    if (state == 2) return;
+    if (state == 0) continue;
+    const long long t0 = clock64();
+    const int rid = r0 + pick;
+    Rep q;
+    rep_bind(q, d, tab, nullptr, rid);  // scalars as saved by the requesting warp (tfalse = 0, new interval_max)
+    q.error = 0;
+    cell_build(q, tid, nt);
+    __syncthreads();
+    nbor_build(q, tid, nt);
+    __syncthreads();
+    cell_clear(q, tid, nt);
+    for (int l = tid; l < q.N; l += nt) redo_lane(q, l);  // events.f:23-107; the requester refreshes the group minima
+    if (q.error && Warp::lane() == 0 && atomicCAS(&q.sc->error, 0, q.error) == 0) q.sc->error_info = q.error_info;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      svc_st_release(d.svc_flag + rid, 0);
+      atomicAdd(&d.svc_ctl[4], (unsigned long long)(clock64() - t0));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, DMD_MIN_CTAS) dmd_event_loop_kernel(DevArrays d, int r0, int nrep, long long n_events, int flags, int n_srv) {
   __shared__ SmemConsts sconst;
   const Staged tab = stage_consts(d, &sconst);
-  int rid = replica_of_warp(r0, nrep);
-  if (rid < 0) return;
+  if ((int)blockIdx.x < n_srv) {
+    svc_serve(d, tab, r0, nrep);
+    return;
+  }
+  const int w = ((int)blockIdx.x - n_srv) * WARPS_PER_CTA + (threadIdx.x >> 5);
+  if (w >= nrep) return;
+  const int rid = r0 + w;
   Rep r;
   rep_bind(r, d, tab, warp_queue(), rid);
+  if (n_srv > 0) r.svc = d.svc_flag + rid;
   if (r.error == 0) run_events(r, n_events, (flags & 1) != 0);
   rep_save(r);
+  if (n_srv > 0 && Warp::lane() == 0) atomicAdd(&d.svc_ctl[0], 1ull);  // the servers leave when all warps are done
 }
 
 // ---- CTA-per-replica engine -----------------------------------------------------------------------------------
@@ -718,7 +779,7 @@ inline int run_grid(const dmd::DevArrays& d, int r0, int nrep, long long n_event
       } else if (hdr.status == 1 && !sc.error && sc.coll < target) {  // one calendar entry for the serial engine
         dmd_bulk_groups_kernel<<<dim3((d.cal_stride / 32 + BULK_THREADS / 32 - 1) / (BULK_THREADS / 32), 1), BULK_THREADS, 0, g_stream>>>(d, rid);
         const auto tc0 = std::chrono::steady_clock::now();
-        dmd_event_loop_kernel<<<1, WARPS_PER_CTA * 32, 0, g_stream>>>(d, rid, 1, 1, 0);
+        dmd_event_loop_kernel<<<1, WARPS_PER_CTA * 32, 0, g_stream>>>(d, rid, 1, 1, 0, 0);
         launches += 2;
         CUDA_OK(cudaGetLastError());
         d2h(&sc, d.scal + rid, sizeof(sc));
@@ -745,7 +806,35 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
     case 0: launch_nbor(d, r0, nrep); launch_predict_all(d, r0, nrep); nl = 5; break;
     case 1: launch_nbor(d, r0, nrep); nl = 3; break;
     case 2: launch_predict_all(d, r0, nrep); nl = 2; break;
-    case 3: dmd_event_loop_kernel<<<grid, block, 0, g_stream>>>(d, r0, nrep, arg, flags); break;
+    case 3: {
+      static bool carve_done = false;  // tuning knob: shared-memory carve-out (percent) of the event-loop kernel
+      if (!carve_done) {
+        carve_done = true;
+        if (const char* cv = getenv("DMDB_CARVEOUT"))
+          CUDA_OK(cudaFuncSetAttribute(dmd_event_loop_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
+      }
+      // service CTAs (see svc_serve): only when they and every worker CTA can be resident at once
+      int n_srv = 0;
+      {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const char* sv = getenv("DMDB_SVC");
+        const int want = sv ? atoi(sv) : (grid >= 32 ? (grid + 7) / 8 : 0);
+        n_srv = want < sms - grid ? want : sms - grid;
+        if (n_srv < 0) n_srv = 0;
+      }
+      if (n_srv > 0) CUDA_OK(cudaMemsetAsync(d.svc_ctl, 0, 8, g_stream));  // finished-warp counter
+      dmd_event_loop_kernel<<<grid + n_srv, block, 0, g_stream>>>(d, r0, nrep, arg, flags, n_srv);
+      if (n_srv > 0 && getenv("DMDB_DEBUG")) {
+        unsigned long long ctl[SVC_CTL_WORDS];
+        d2h(ctl, d.svc_ctl, sizeof(ctl));
+        fprintf(stderr, "service: %d CTAs, %llu worker warps done, %.3f ms of service time per CTA\n", n_srv, ctl[0],
+                (double)ctl[4] / n_srv / 1.9e6);
+        CUDA_OK(cudaMemsetAsync(d.svc_ctl, 0, sizeof(ctl), g_stream));
+      }
+      break;
+    }
     case 4: dmd_sync_positions_kernel<<<grid, block, 0, g_stream>>>(d, r0, nrep); break;
     case 5: dmd_energy_kernel<<<grid, block, 0, g_stream>>>(d, r0, nrep, eout); break;
     case 6: dmd_evcode_kernel<<<((int)arg + 127) / 128, 128, 0, g_stream>>>(d, r0, (int)arg, ibuf); break;

@@ -46,6 +46,7 @@ struct Rep {
   EventLogRec* log;
   OutRec* out;
   int32_t* cq;  // cascade queue storage (shared memory on the device)
+  int32_t* svc;  // this replica's request word of the list-rebuild service, or nullptr: rebuild in place
   // scalars cached in registers (identical in every lane)
   double t, tfalse, old_tfalse, setemp, interval, t_fact, interval_max, n_forced, avegtime;
   int64_t coll;
@@ -78,36 +79,37 @@ DMD_DEV Staged staged_global(const DevArrays& d) {
 }
 
 DMD_DEV void rep_bind(Rep& r, const DevArrays& d, const Staged& st, int32_t* cq, int rid) {
-  const SysConst* s = d.sys;
-  r.c.sys = s;
+  // sizes and strides come from the kernel parameters (constant bank), not from *d.sys: every base below is then
+  // a function of rid and constants only, which the compiler can recompute instead of spilling
+  r.c.sys = d.sys;
   r.c.tab = st.tab;
   r.c.hot = st.hot;
   r.c.bl = st.bl;
   r.c.meta = d.meta;
   r.c.chain = d.chain;
-  const int N = s->N;
+  const int N = d.n_beads, cap = d.cap;
   r.N = N;
-  r.cap = s->cap;
-  r.G = s->ngroups;
+  r.cap = cap;
+  r.G = d.ngroups;
   const size_t rr = (size_t)rid;
   r.rec = d.rec + rr * N;
   r.cal = d.cal + rr * d.cal_stride;
   r.er34 = d.er34 + rr * 2 * N;
-  r.up = d.up + rr * N * s->cap;
-  r.dn = d.dn + rr * N * s->cap;
+  r.up = d.up + rr * N * cap;
+  r.dn = d.dn + rr * N * cap;
   r.nup = d.nup + rr * N;
   r.ndn = d.ndn + rr * N;
   r.oldr = d.oldr + rr * 3 * N;
-  const size_t ncc = (size_t)((s->ncr + 1) >> 1), nc3 = ncc * ncc * ncc;
-  r.cellhead = d.cellhead + rr * nc3;
+  r.cellhead = d.cellhead + rr * (size_t)d.ncc3;
   r.cpk = d.cpk + rr * N;
   r.cnext = d.cnext + rr * N;
   r.cellof = d.cellof + rr * N;
-  r.tmin1 = d.tmin1 + rr * s->ngroups;
+  r.tmin1 = d.tmin1 + rr * d.ngroups;
   r.sc = d.scal + rr;
-  r.log = d.log + rr * (s->log_cap > 0 ? s->log_cap : 1);
-  r.out = d.out + rr * s->out_cap;
+  r.log = d.log + rr * (d.log_cap > 0 ? d.log_cap : 1);
+  r.out = d.out + rr * d.out_cap;
   r.cq = cq;
+  r.svc = nullptr;
   r.dirty0 = r.dirty1 = 0;
   rep_load_scalars(r);
 }
@@ -1033,6 +1035,64 @@ DMD_DEV void nbor(Rep& r) {  // nbor.f:33-137
   cell_clear(r);
 }
 
+#if !defined(DMD_HOST_TRACE)
+// ---- list-rebuild service (device only).  A warp whose replica needs nbor() + events() publishes the request
+// in its svc word and sleeps; a service CTA on another SM claims it (1 -> 2), rebuilds with all its threads and
+// clears the word.  release/acquire at gpu scope on the word orders the replica's arrays between the two SMs (the
+// acquire also drops the stale L1 lines).  A request nobody claims within SVC_PATIENCE cycles is taken back
+// (1 -> 3) and served in place, so the loop never depends on a service CTA being resident.
+constexpr long long SVC_PATIENCE = 4000000;      // ~2 ms
+constexpr long long SVC_TIMEOUT = 4000000000ll;  // ~2 s in state 2: report an error instead of hanging
+DMD_DEV int svc_ld_relaxed(const int32_t* p) {  // polling: no L1 invalidation (the other warps of the SM keep their lines)
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+DMD_DEV void svc_fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+DMD_DEV void svc_st_release(int32_t* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+DMD_DEV int svc_cas_acq_rel(int32_t* p, int cmp, int val) {
+  int old;
+  asm volatile("atom.acq_rel.gpu.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+// returns true when a service CTA has rebuilt lists and calendar, false when the warp has to do it in place
+DMD_COLD bool svc_request(Rep r) {
+  __threadfence();  // every lane's writes (wrapped positions, oldr, scalars) before the request becomes visible
+  Warp::sync();
+  int res = 0;  // 0 served, 1 in place, 2 time-out
+  if (Warp::lane() == 0) {
+    svc_st_release(r.svc, 1);
+    const long long t0 = clock64();
+    while (true) {
+      const int v = svc_ld_relaxed(r.svc);
+      if (v == 0) {
+        svc_fence_acquire();  // once: orders the service CTA's writes before this warp's reads, drops stale L1 lines
+        break;
+      }
+      const long long dt = clock64() - t0;
+      if (v == 1 && dt > SVC_PATIENCE && svc_cas_acq_rel(r.svc, 1, 3) == 1) {
+        res = 1;
+        break;
+      }
+      if (dt > SVC_TIMEOUT) {
+        res = 2;
+        break;
+      }
+      __nanosleep(1500);
+    }
+  }
+  res = Warp::shfl(res, 0);
+  if (res == 2) {
+    if (Warp::lane() == 0) {
+      r.sc->error = DMD_E_SERVICE;
+      r.sc->error_info = 0;
+    }
+    Warp::sync();
+  }
+  return res != 1;
+}
+#endif
+
 // ---- cold pseudo-events: they work on a by-value copy of the view and hand the scalars back through r.sc
 // main.F90:997-1049
 DMD_COLD void ghost_event_cold(Rep r) {
@@ -1127,8 +1187,22 @@ DMD_COLD void interval_event_cold(Rep r) {
       r.oldr[3 * k] = x; r.oldr[3 * k + 1] = y; r.oldr[3 * k + 2] = z;
     }
     Warp::sync();
-    nbor(r);
-    predict_all(r);  // events(); every bead's (tim, nptnr, coltype) is re-derived from interval_max+ltstep
+    bool in_place = true;
+#if !defined(DMD_HOST_TRACE)
+    if (r.svc) {  // hand nbor() + events() to a service CTA (another SM); the view's scalars travel through r.sc
+      rep_save(r);
+      in_place = !svc_request(r);
+      r.error = r.sc->error;  // a service CTA reports list overflow etc. through the stored scalars
+      r.error_info = r.sc->error_info;
+    }
+#endif
+    if (in_place) {
+      nbor(r);
+      predict_all(r);  // events(); every bead's (tim, nptnr, coltype) is re-derived from interval_max+ltstep
+#if !defined(DMD_HOST_TRACE)
+      if (r.svc && Warp::lane() == 0) *r.svc = 0;  // taken back (state 3): nobody else touches the word
+#endif
+    }
   }
   if (Warp::lane() == 0) r.cal[N + 1].t = r.interval * 0.999;  // :1181
   Warp::sync();

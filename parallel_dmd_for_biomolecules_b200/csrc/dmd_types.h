@@ -121,6 +121,7 @@ constexpr int DMD_E_CAL_EMPTY = 2;  // calendar has no finite entry
 constexpr int DMD_E_NEG_TIME = 3;   // tij < -1e-10 (events.f:59-73 debugging guard)
 constexpr int DMD_E_GRID = 4;       // bead outside the cell grid
 constexpr int DMD_E_BAD_INPUT = 5;  // bptnr entry out of range (run start)
+constexpr int DMD_E_SERVICE = 6;    // the list-rebuild service did not answer (event loop, dmd_cuda.cu)
 
 // one calendar entry: tim(k), nptnr(k), coltype(k) of header.f:20-22,47 side by side so that popping the
 // minimum delivers the whole event in one access.  type: low 8 bits coltype (as int8), bits 8-15 the static
@@ -176,6 +177,16 @@ struct DevArrays {
   int32_t n_beads;        // N (host-side copy of sys->N)
   int32_t nres;           // residues over both species (rows of bl)
   int32_t n_nc;           // entries of nc_beads
+  // copies of the SysConst fields the per-replica address arithmetic needs: as kernel parameters they sit in the
+  // constant bank, so a replica's array bases can be recomputed instead of being held (or spilled) in registers
+  int32_t cap, ngroups, log_cap, out_cap;
+  int32_t ncc3;           // coarse cells per replica (entries of cellhead)
+  // list-rebuild service of the warp-per-replica engine (dmd_cuda.cu: a few CTAs of the event-loop kernel do the
+  // neighbour-list + calendar rebuilds for the warps of all other CTAs, so that the event-loop SMs keep only the
+  // hot loop in their 32 KB instruction caches)
+  int32_t* svc_flag;      // per replica: 0 idle, 1 rebuild requested, 2 being served, 3 taken back by its own warp
+  unsigned long long* svc_ctl;  // [0] finished worker warps [1] requests [2] served locally [3] wait cycles [4] service cycles
 };
+constexpr int SVC_CTL_WORDS = 8;
 
 }  // namespace dmd
