@@ -157,6 +157,11 @@ int dmdb_create(const dmdb_params* p, const dmdb_topology* topo, const dmdb_tabl
     int32_t* dchain = dalloc<int32_t>(h.get(), N);
     be::h2d(dchain, h->model.chain.data(), N * 4);
     d.chain = dchain;
+    if (!h->model.sctab.empty()) {
+      uint8_t* dsct = dalloc<uint8_t>(h.get(), h->model.sctab.size());
+      be::h2d(dsct, h->model.sctab.data(), h->model.sctab.size());
+      d.sctab = dsct;
+    }
     d.rec = dalloc<dmd::BeadRec>(h.get(), R * N);
     d.cal = dalloc<dmd::CalEnt>(h.get(), R * d.cal_stride);
     d.er34 = dalloc<int32_t>(h.get(), R * 2 * N);

@@ -87,6 +87,7 @@ DMD_DEV void rep_bind(Rep& r, const DevArrays& d, const Staged& st, int32_t* cq,
   r.c.bl = st.bl;
   r.c.meta = d.meta;
   r.c.chain = d.chain;
+  r.c.sctab = d.sctab;
   const int N = d.n_beads, cap = d.cap;
   r.N = N;
   r.cap = cap;
@@ -815,8 +816,9 @@ DMD_COLD ColdRes pair_event_cold(Rep r, int i, int j, int ct, int code) {
   return res;
 }
 
-// worker block main.F90:1429-1959 with current state, then master main.F90:926,943
-DMD_DEV void pair_event(Rep& r, int i, const CalEnt& ev) {
+// worker block main.F90:1429-1959 with current state, then master main.F90:926; the re-prediction (:943) is done
+// by the caller.  Returns xpulse_del.
+DMD_DEV bool pair_event(Rep& r, int i, const CalEnt& ev) {
   const int j = ev.ptnr;
   int ct = type_of(ev.type);
   bool xpulse_del = false;
@@ -841,7 +843,7 @@ DMD_DEV void pair_event(Rep& r, int i, const CalEnt& ev) {
   }
   if (Warp::lane() == 0 && ct >= 0 && ct < 32) r.sc->nevents[ct] += 1;  // main.F90:926
   log_event(r, i, j, ct, code);
-  partial_events(r, i, j, xpulse_del);  // main.F90:943
+  return xpulse_del;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -972,9 +974,14 @@ DMD_DEV void nbor_build(Rep& r, int t0 = Warp::lane(), int ts = DMD_W) {
     const BeadRec rk = r.rec[k];
     const uint32_t mk = r.c.meta[k];
     const int ck = r.c.chain[k];
+    // same-chain pairs (most candidates): class from the per-species table instead of the closed form
+    const int sct0 = r.c.sctab ? s.sct_off[meta_sp(mk)] : -1;
+    const uint8_t* const sct_row = sct0 >= 0 ? r.c.sctab + sct0 + (size_t)meta_local(mk) * s.numbeads[meta_sp(mk)] : nullptr;
     int nu = 0, nd = 0;
     auto test_and_append = [&](int j) {
-      const int sc = static_code(s, mk, ck, k, r.c.meta[j], r.c.chain[j], j);
+      const uint32_t mj = r.c.meta[j];
+      const int cj = r.c.chain[j];
+      const int sc = (sct_row && cj == ck) ? (int)sct_row[meta_local(mj)] : static_code(s, mk, ck, k, mj, cj, j);
       bool in;
       if (code_is_bonded_class(sc)) {
         in = true;  // nbor.f:60
@@ -1094,8 +1101,9 @@ DMD_COLD bool svc_request(Rep r) {
 #endif
 
 // ---- cold pseudo-events: they work on a by-value copy of the view and hand the scalars back through r.sc
-// main.F90:997-1049
-DMD_COLD void ghost_event_cold(Rep r) {
+// main.F90:997-1048; returns the bead that got its new velocity -- the caller re-predicts it (:1049) with the hot
+// loop's own copy of partial_events, so that a ghost event does not drag a second copy through the instruction cache
+DMD_COLD int ghost_event_cold(Rep r) {
   const int N = r.N;
   int i;
   do {
@@ -1135,12 +1143,10 @@ DMD_COLD void ghost_event_cold(Rep r) {
     r.cal[N].t = tnext;
     r.sc->numghosts += 1;
   }
-  mark_dirty(r, N >> 5);
   if (r.tfalse < r.old_tfalse) r.tfalse = r.old_tfalse;  // main.F90:1047
   log_event(r, N, i, -2, 0);
-  partial_events(r, i, -1, false);
-  flush_dirty(r);
   rep_save(r);
+  return i;
 }
 
 // main.F90:1126-1187
@@ -1286,17 +1292,26 @@ DMD_COLD void output_event_cold(Rep r) {
 DMD_DEV void process_one(Rep& r, int o, const CalEnt& ev) {
   r.tfalse = ev.t;
   r.coll += 1;
+  int pi = o, pj = ev.ptnr;  // the bead(s) whose events have to be re-predicted (partial_events.f)
+  bool xpulse_del = false, redo = true;
   if (o < r.N) {
-    pair_event(r, o, ev);
+    xpulse_del = pair_event(r, o, ev);
   } else {
     rep_save(r);  // hand the scalars to the out-of-line handler through r.sc ...
-    if (o == r.N) ghost_event_cold(r);
-    else if (o == r.N + 1) interval_event_cold(r);
-    else output_event_cold(r);
+    if (o == r.N) {
+      pi = ghost_event_cold(r);
+      pj = -1;
+    } else {
+      redo = false;
+      if (o == r.N + 1) interval_event_cold(r);
+      else output_event_cold(r);
+    }
     Warp::sync();
     rep_load_scalars(r);  // ... and take them back
     r.dirty0 = r.dirty1 = 0;
+    if (redo) mark_dirty(r, r.N >> 5);  // the next ghost time
   }
+  if (redo) partial_events(r, pi, pj, xpulse_del);  // main.F90:943, :1049 -- the only call site in the loop
   r.old_tfalse = r.tfalse;
 }
 

@@ -25,6 +25,7 @@ struct HostModel {
   std::vector<int32_t> chain;
   std::vector<uint8_t> id0;
   std::vector<int32_t> nc_beads;  // indices of the N and C beads (ascending): the only H-bond capable ones
+  std::vector<uint8_t> sctab;     // static_code() over one chain of each species (chains of <= 256 beads)
   dmdb_params params;
 };
 
@@ -190,6 +191,18 @@ inline void build_model(const dmdb_params& p, const dmdb_topology& topo, const d
         m.id0[bead] = (uint8_t)id;
         if (cls == 1 || cls == 2) m.nc_beads.push_back(bead);
       }
+  }
+  // ---- same-chain class table for the list rebuild: static_code() of every bead pair of the first chain of a species
+  s.sct_off[0] = s.sct_off[1] = -1;
+  m.sctab.clear();
+  for (int sp = 0, first = 0; sp < topo.n_species; first += s.nch[sp] * s.numbeads[sp], sp++) {
+    const int nbd = s.numbeads[sp];
+    if (s.nch[sp] < 1 || nbd > 256) continue;
+    s.sct_off[sp] = (int)m.sctab.size();
+    for (int a = 0; a < nbd; a++)
+      for (int b = 0; b < nbd; b++)
+        m.sctab.push_back(a == b ? 0 : (uint8_t)static_code(s, m.meta[first + a], m.chain[first + a], first + a, m.meta[first + b],
+                                                           m.chain[first + b], first + b));
   }
   // ---- nbor_setup.f:13-118 (first chain of each species against itself and each other)
   double sig_max[51] = {0}, sig_max_all = 0.0;

@@ -19,6 +19,7 @@ struct Ctx {                 // read-only context of one warp
   const double* bl;          // per-residue side-chain bond windows (shared memory when nres <= HOT_MAX_RES)
   const uint32_t* meta;
   const int32_t* chain;
+  const uint8_t* sctab;      // same-chain static classes (list rebuild), or nullptr
 };
 
 DMD_DEV int tix(int idi, int idj) { return (idi - 1) * 28 + (idj - 1); }

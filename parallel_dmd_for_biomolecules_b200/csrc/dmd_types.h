@@ -85,6 +85,7 @@ struct SysConst {
   int32_t cap;               // per-bead capacity of each neighbour list
   int32_t ngroups;           // ceil((N+3)/32) calendar groups
   int32_t log_cap, out_cap;
+  int32_t sct_off[2];        // offsets of the species' rows in the same-chain class table (DevArrays.sctab), -1: none
   double ev_param1[51];      // make_code.f:18-39 (squeeze factors), index = ev_code
   double ev_param2[51];      // blmin of codes 4-9 (make_code.f:49-57)
   double ev_param3[51];      // blmax
@@ -154,6 +155,7 @@ struct DevArrays {
   const double* bl;       // nres x 6: per-residue side-chain bond windows (min,max of codes 10, 11, 12), bond.f:82-91
   const uint32_t* meta;   // N
   const int32_t* chain;   // N (global chain index)
+  const uint8_t* sctab;   // static_code() of every bead pair of ONE chain of each species, [local_a * numbeads + local_b]
   // per replica
   BeadRec* rec;           // N
   CalEnt* cal;            // N+3 entries padded to ngroups*32 (padding t = 1e300)
