@@ -179,6 +179,17 @@ int dmdb_potential_energies(dmdb_handle* h, double* epot /* n_replicas */, doubl
  * on the device; H-bond state is kept.  Entries <= 0 leave the replica untouched. */
 int dmdb_apply_temperatures(dmdb_handle* h, const double* tstar_new /* n_replicas */);
 
+
+/* Engine 1 tuning (no reference counterpart).  The event-loop kernel gives a few of its CTAs the role of a LIST-REBUILD
+ * SERVICE: they run nbor() + events() (nbor.f:33-137, events.f:23-107) for the warps of all other CTAs, so that the
+ * SMs running the event loop keep only the hot loop in their 32 KB instruction caches.
+ * dmdb_device_fill: the replica count that fills `device` in one wave with the default split, and that split.
+ * dmdb_set_service_ctas: n = -1 automatic (default: service CTAs whenever they and every event-loop CTA can be
+ * resident at once), 0 = every warp rebuilds its own lists, n > 0 = that many service CTAs.  Results do not depend
+ * on the setting. */
+int dmdb_device_fill(int device, int32_t* n_replicas, int32_t* n_service_ctas);
+int dmdb_set_service_ctas(dmdb_handle* h, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,7 @@ struct dmdb_handle {
   std::string err;
   double last_ms = 0;
   int last_launches = 0;
+  int service_ctas = -1;  // dmdb_set_service_ctas
 };
 
 namespace {
@@ -306,6 +307,24 @@ int dmdb_predict_all(dmdb_handle* h) {
 
 int dmdb_get_replica_stats(dmdb_handle* h, int replica, dmdb_stats* s);
 
+int dmdb_set_service_ctas(dmdb_handle* h, int n) {
+  if (!h) return DMDB_ERR_ARG;
+  if (n < -1 || n > 0xfffe) return fail(h, DMDB_ERR_ARG, "service CTAs: -1 (automatic), 0 (none) or a positive count");
+  h->service_ctas = n;
+  return DMDB_OK;
+}
+
+int dmdb_device_fill(int device, int32_t* n_replicas, int32_t* n_service_ctas) {
+  if (!n_replicas) return fail(nullptr, DMDB_ERR_ARG, "null argument");
+  std::string err;
+  if (!be::init(device, err)) return fail(nullptr, DMDB_ERR_NO_DEVICE, err);
+  int workers = 0, service = 0;
+  be::device_fill(workers, service);
+  *n_replicas = workers;
+  if (n_service_ctas) *n_service_ctas = service;
+  return DMDB_OK;
+}
+
 static int run_impl(dmdb_handle* h, int64_t n_events, dmdb_stats* stats, int flags);
 int dmdb_run(dmdb_handle* h, int64_t n_events, dmdb_stats* stats) { return run_impl(h, n_events, stats, 0); }
 int dmdb_run_until_output(dmdb_handle* h, int64_t max_events, dmdb_stats* stats) { return run_impl(h, max_events, stats, 1); }
@@ -323,7 +342,8 @@ static int run_impl(dmdb_handle* h, int64_t n_events, dmdb_stats* stats, int fla
   if (engine == 3 && (flags || !be::grid_engine_available())) engine = 2;  // (run_until_output: engines 1 and 2)
   if (engine == 2 && !be::block_engine_fits(h->model.sys)) engine = 1;
   const int op = engine == 3 ? dmd::OP_RUN_GRID : (engine == 2 ? dmd::OP_RUN_BLOCK : dmd::OP_RUN);
-  DMDB_TRY(h, be::run_op(h->d, op, 0, h->d.n_replicas, n_events, nullptr, nullptr, &h->last_ms, &h->last_launches, flags);)
+  const int svc_bits = op == dmd::OP_RUN ? ((h->service_ctas + 1) & 0xffff) << 8 : 0;  // run_op: bits 8-23 = 1 + service CTAs (0 = automatic)
+  DMDB_TRY(h, be::run_op(h->d, op, 0, h->d.n_replicas, n_events, nullptr, nullptr, &h->last_ms, &h->last_launches, flags | svc_bits);)
   rc = check_device_errors(h);
   if (rc) return rc;
   if (stats) return dmdb_get_replica_stats(h, -1, stats);

@@ -793,6 +793,24 @@ inline bool block_engine_fits(const dmd::SysConst& s) {
   return dmd::blk_layout(s.N, s.ngroups * 32, smem_optin()).total <= smem_optin();
 }
 
+// Service split of the event-loop kernel (measured on B200, 48-peptide box, 180 us per rebuild: 12 service CTAs
+// 1.49e8, 16: 1.48e8, 20: 1.69e8, 24: 1.72e8 events/s; no service: 1.38e8): about one service CTA per five
+// event-loop CTAs
+inline int sm_count() {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+inline int default_service_ctas(int worker_ctas) { return worker_ctas >= 32 ? (worker_ctas * 10 + 51) / 52 : 0; }
+inline void device_fill(int& replicas, int& service) {
+  const int sms = sm_count();
+  int w = sms;
+  while (w > 1 && w + default_service_ctas(w) > sms) w--;
+  replicas = w * dmd::WARPS_PER_CTA;
+  service = default_service_ctas(w);
+}
+
 inline dim3 bulk_grid(const dmd::DevArrays& d, int nrep, int n) { return dim3((n + dmd::BULK_THREADS - 1) / dmd::BULK_THREADS, nrep); }
 inline void launch_nbor(const dmd::DevArrays& d, int r0, int nrep) {  // = nbor(): cell_add.f + nbor.f
   using namespace dmd;
@@ -951,14 +969,14 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
       // service CTAs (dmd_rebuild_service_kernel): only when they and every worker CTA can be resident at once
       int n_srv = 0;
       {
-        int dev = 0, sms = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const char* sv = getenv("DMDB_SVC");
-        const int want = sv ? atoi(sv) : (grid >= 32 ? (grid + 7) / 8 : 0);
+        const int sms = sm_count();
+        const int asked = ((flags >> 8) & 0xffff) - 1;  // dmdb_set_service_ctas; -1 = automatic
+        const char* sv = getenv("DMDB_SVC");          // tuning override
+        const int want = sv ? atoi(sv) : (asked >= 0 ? asked : default_service_ctas(grid));
         n_srv = want < sms - grid ? want : sms - grid;
         if (n_srv < 0) n_srv = 0;
       }
+      flags &= 0xff;
       const char* svm = getenv("DMDB_SVC_MODE");
       const bool two_kernels = svm && atoi(svm) == 2;
       if (n_srv > 0 && !two_kernels) CUDA_OK(cudaMemsetAsync(d.svc_ctl, 0, SVC_CTL_WORDS * 8, g_stream));

@@ -896,9 +896,10 @@ DMD_DEV bool in_fine_stencil(uint32_t pk, uint32_t pj, int ncr) {
   return dx <= 2 && dy <= 2 && dz <= 2;
 }
 
-// f(j) for every bead j != k whose cell lies in the 5 x 5 x 5 block around the cell of bead k
+// f(j) for every bead j != k whose cell lies in the 5 x 5 x 5 block around the cell of bead k; beads with index in
+// [skip_lo, skip_hi) are passed over (nbor_build handles the beads of k's own chain without the cell grid)
 template <class F>
-DMD_DEV void stencil_visit(const Rep& r, int k, F f) {
+DMD_DEV void stencil_visit(const Rep& r, int k, F f, int skip_lo = 0, int skip_hi = 0) {
   const int ncr = r.c.sys->ncr, ncc = coarse_dim(ncr);
   const uint32_t pk = r.cpk[k];
   int xs[4], ys[4], zs[4];
@@ -924,7 +925,7 @@ DMD_DEV void stencil_visit(const Rep& r, int k, F f) {
         j = ix == 1 ? h1 : (ix == 2 ? h2 : h3);
         continue;
       }
-      if (j != k && in_fine_stencil(pk, r.cpk[j], ncr)) f(j);
+      if (j != k && (j < skip_lo || j >= skip_hi) && in_fine_stencil(pk, r.cpk[j], ncr)) f(j);
       j = r.cnext[j];
     }
   }
@@ -978,10 +979,7 @@ DMD_DEV void nbor_build(Rep& r, int t0 = Warp::lane(), int ts = DMD_W) {
     const int sct0 = r.c.sctab ? s.sct_off[meta_sp(mk)] : -1;
     const uint8_t* const sct_row = sct0 >= 0 ? r.c.sctab + sct0 + (size_t)meta_local(mk) * s.numbeads[meta_sp(mk)] : nullptr;
     int nu = 0, nd = 0;
-    auto test_and_append = [&](int j) {
-      const uint32_t mj = r.c.meta[j];
-      const int cj = r.c.chain[j];
-      const int sc = (sct_row && cj == ck) ? (int)sct_row[meta_local(mj)] : static_code(s, mk, ck, k, mj, cj, j);
+    auto append_with_class = [&](int j, int sc) {
       bool in;
       if (code_is_bonded_class(sc)) {
         in = true;  // nbor.f:60
@@ -1006,21 +1004,44 @@ DMD_DEV void nbor_build(Rep& r, int t0 = Warp::lane(), int ts = DMD_W) {
         }
       }
     };
+    auto test_and_append = [&](int j) {
+      const uint32_t mj = r.c.meta[j];
+      const int cj = r.c.chain[j];
+      const int sc = (sct_row && cj == ck) ? (int)sct_row[meta_local(mj)] : static_code(s, mk, ck, k, mj, cj, j);
+      append_with_class(j, sc);
+    };
     if (r.cnext[k] != -2) {
+      // (0) short chains: the beads of k's own chain -- most of its neighbours, a contiguous index range with known
+      // classes -- are tested directly (same criterion: inside the 5 x 5 x 5 block, then class / distance rule);
+      // the lanes of a warp hold beads of the same chain, so these loads are broadcasts and the loop is convergent
+      int own_lo = 0, own_hi = 0;
+      if (sct_row && s.numbeads[meta_sp(mk)] <= 64) {
+        const int nb = s.numbeads[meta_sp(mk)], ncr = s.ncr;
+        own_lo = k - meta_local(mk);
+        own_hi = own_lo + nb;
+        const uint32_t pk = r.cpk[k];
+        // entries of the down list go to the front of the row the candidates are parked in: parked ones start behind
+        for (int lj = 0; lj < nb; lj++) {
+          const int j = own_lo + lj;
+          if (j == k || r.cnext[j] == -2 || !in_fine_stencil(pk, r.cpk[j], ncr)) continue;
+          append_with_class(j, (int)sct_row[lj]);
+        }
+      }
       // two steps, so that the lanes of a warp run the expensive test in lockstep: (1) walk the cells and park
-      // the candidates in the bead's (still unused) down-list row, (2) test them one after the other.  Writing
-      // entry nd of the row is safe: nd never exceeds the number of candidates already consumed.
+      // the candidates in the bead's down-list row behind the entries it already holds, (2) test them one after
+      // the other.  Writing entry nd of the row is safe: nd never exceeds the number of slots already consumed.
       uint32_t* park = r.dn + (size_t)k * cap;
+      const int p0 = nd;  // down entries of the own chain stay in front
       int nc = 0;
       stencil_visit(r, k, [&](int j) {
-        if (nc < cap) park[nc] = (uint32_t)j;
+        if (p0 + nc < cap) park[p0 + nc] = (uint32_t)j;
         nc++;
-      });
-      if (nc <= cap) {
+      }, own_lo, own_hi);
+      if (p0 + nc <= cap) {
 #pragma unroll 1
-        for (int t = 0; t < nc; t++) test_and_append((int)park[t]);
+        for (int t = 0; t < nc; t++) test_and_append((int)park[p0 + t]);
       } else {  // more candidates than a row holds (very dense region): test them on the fly
-        stencil_visit(r, k, test_and_append);
+        stencil_visit(r, k, test_and_append, own_lo, own_hi);
       }
     }
     if (nu > cap || nd > cap) {

@@ -28,7 +28,19 @@ SYMBOLS = [
     "dmdb_get_nbors", "dmdb_get_calendar", "dmdb_get_state", "dmdb_get_evcode", "dmdb_energy_of",
     "dmdb_get_event_log", "dmdb_get_replica_stats", "dmdb_potential_energies", "dmdb_set_state_all",
     "dmdb_get_state_all", "dmdb_apply_temperatures", "dmdb_get_batch_stats", "dmdb_run_until_output",
+    "dmdb_device_fill", "dmdb_set_service_ctas",
 ]
+
+
+def device_fill(device: int = 0, lib_path: Optional[str] = None):
+    """(replicas, service CTAs): the replica count that fills `device` in one wave of the warp-per-replica engine
+    with the default list-rebuild service split (dmdb_device_fill)"""
+    lib = load_library(lib_path)
+    nr, ns = C.c_int32(0), C.c_int32(0)
+    rc = lib.dmdb_device_fill(int(device), C.byref(nr), C.byref(ns))
+    if rc != 0:
+        raise DMDError(rc, (lib.dmdb_last_error(None) or b"").decode())
+    return nr.value, ns.value
 
 
 class DMDError(RuntimeError):
@@ -213,6 +225,11 @@ class DMD:
         self._chk(self._l.dmdb_get_event_log(self._h, replica, C.c_int64(first), C.c_int64(n),
                                              out.ctypes.data_as(C.POINTER(Event)), C.byref(n_out)))
         return out[: n_out.value]
+
+    def set_service_ctas(self, n: int = -1):
+        """engine 1: CTAs of the event-loop kernel that only rebuild neighbour lists + calendars for the others
+        (-1 automatic, 0 none); results do not depend on it"""
+        self._chk(self._l.dmdb_set_service_ctas(self._h, int(n)))
 
     def batch_stats(self, replica=-1) -> dict:
         """batching statistics of the CTA-per-replica engine (engine=2)"""

@@ -22,6 +22,7 @@ module dmdb200
   public :: dmdb_get_cells, dmdb_get_nbors, dmdb_get_calendar, dmdb_get_state, dmdb_get_evcode
   public :: dmdb_energy_of, dmdb_get_event_log, dmdb_get_replica_stats
   public :: dmdb_potential_energies, dmdb_apply_temperatures, dmdb_get_batch_stats
+  public :: dmdb_device_fill, dmdb_set_service_ctas
   public :: dmdb_error_message
   public :: DMDB_OK, DMDB_ERR_ARG, DMDB_ERR_NO_DEVICE, DMDB_ERR_CUDA, DMDB_ERR_STATE, DMDB_ERR_CAPACITY, &
             DMDB_ERR_PHYSICS, DMDB_MAX_SPECIES
@@ -251,6 +252,18 @@ module dmdb200
       import :: c_ptr, c_int, c_double
       type(c_ptr), value :: handle
       real(c_double), intent(in) :: tstar_new(*)
+      integer(c_int) :: rc
+    end function
+    function dmdb_device_fill(device, n_replicas, n_service_ctas) bind(C, name="dmdb_device_fill") result(rc)
+      import :: c_int, c_int32_t
+      integer(c_int), value :: device
+      integer(c_int32_t), intent(out) :: n_replicas, n_service_ctas
+      integer(c_int) :: rc
+    end function
+    function dmdb_set_service_ctas(handle, n) bind(C, name="dmdb_set_service_ctas") result(rc)
+      import :: c_ptr, c_int
+      type(c_ptr), value :: handle
+      integer(c_int), value :: n
       integer(c_int) :: rc
     end function
   end interface

@@ -96,6 +96,7 @@ inline void fill_i32(int32_t* d, int v, size_t n) {
 }
 inline bool block_engine_fits(const dmd::SysConst&) { return true; }
 inline bool grid_engine_available() { return false; }  // device only
+inline void device_fill(int& replicas, int& service) { replicas = 1; service = 0; }
 inline void run_init(const dmd::DevArrays& d, int r0, int nrep, const double* sv, size_t sv_stride, const int32_t* bp,
                      size_t bp_stride, const double* tstar, unsigned long long seed0) {
   using namespace dmd;
