@@ -4,7 +4,8 @@
 Metric (BASELINE.json): DMD collision events/s per B200 (every processed calendar event, counted like the
 reference's `coll`, main.F90:639).  Workload at N=1: BASELINE config 2 -- the 48-peptide Abeta16-22 (KLVFFAE)
 PRIME20 box, N = 1344 beads, L = 158.54 A, T* = 0.18, Andersen thermostat on (-Dcanon) -- as an ensemble of R
-independent replicas resident on one GPU (one warp per replica).  N>1: the same per-GPU workload on every GPU
+independent replicas resident on one GPU (one warp per replica; the replica count is the one that fills the device in
+one wave next to the list-rebuild service CTAs of the same kernel, dmdb_device_fill).  N>1: the same per-GPU workload on every GPU
 (weak scaling) plus one replica-exchange collective (NCCL all-gather of (E_pot, T*)) per step.
 
 A "step" = every replica advances `--events` calendar events (one launch of the persistent event-loop kernel).
@@ -44,7 +45,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--replicas", type=int, default=4144, help="replicas per GPU (148 SMs x 28 warps)")
+    ap.add_argument("--replicas", type=int, default=0, help="replicas per GPU (0 = dmdb_device_fill: one 28-warp CTA per "
+                    "SM minus the list-rebuild service CTAs, 3584 on a 148-SM B200)")
     ap.add_argument("--events", type=int, default=20000, help="calendar events per replica per step")
     ap.add_argument("--ref-events", type=int, default=400000, help="events per host thread per step (--impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -241,7 +243,7 @@ def main():
     import torch.distributed as dist
 
     from parallel_dmd_for_biomolecules_b200 import genconfig, replica_exchange, tables
-    from parallel_dmd_for_biomolecules_b200.dmd import DMD
+    from parallel_dmd_for_biomolecules_b200.dmd import DMD, device_fill
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
@@ -257,6 +259,9 @@ def main():
 
     tab = tables.load_default_tables()
     topo, sv = genconfig.system_b(tab, TSTAR, seed=1)
+    fill_replicas, service_ctas = device_fill(local_rank)
+    if args.replicas <= 0:
+        args.replicas = fill_replicas
     N, R, E = topo.n_beads, args.replicas, args.events
     p = tables.make_params(boxl=BOXL, tstar=TSTAR, canon=True, n_replicas=R, device=local_rank, seed=1058472402 + 100003 * rank)
     d = DMD(p, topo, tab)
@@ -331,8 +336,10 @@ def main():
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "replicas_per_gpu": R, "beads_per_replica": N, "events_per_replica_per_step": E,
-                       "parallelism": "one warp per replica, %d replicas per GPU, %d GPU(s)%s" % (
-                           R, world, ", NCCL all-gather replica exchange per step" if world > 1 else ""),
+                       "parallelism": "one warp per replica, %d replicas per GPU, %d GPU(s)%s; per GPU %d event-loop CTAs + "
+                                      "%s list-rebuild service CTAs in ONE kernel" % (
+                           R, world, ", NCCL all-gather replica exchange per step" if world > 1 else "",
+                           (R + 27) // 28, service_ctas if R == fill_replicas else "auto"),
                        "l2": "no flush needed: resident working set per GPU %.1f GB >> 126 MB L2" % (R * N * 1100 / 1e9),
                        "event_count_convention": "all calendar events incl. ghost/interval pseudo-events (main.F90:639)",
                        "pair_event_fraction": d_pair / max(d_events, 1),

@@ -793,16 +793,16 @@ inline bool block_engine_fits(const dmd::SysConst& s) {
   return dmd::blk_layout(s.N, s.ngroups * 32, smem_optin()).total <= smem_optin();
 }
 
-// Service split of the event-loop kernel (measured on B200, 48-peptide box, 180 us per rebuild: 12 service CTAs
-// 1.49e8, 16: 1.48e8, 20: 1.69e8, 24: 1.72e8 events/s; no service: 1.38e8): about one service CTA per five
-// event-loop CTAs
+// Service split of the event-loop kernel (measured on B200, 48-peptide box, 158 us per rebuild, 148 CTAs in all:
+// 8 service CTAs 1.45e8, 12: 1.53e8, 16: 1.57e8, 18: 1.74e8, 20: 1.755e8, 22: 1.74e8, 24: 1.72e8 events/s; without
+// the service 1.38e8): about one service CTA per 6.4 event-loop CTAs
 inline int sm_count() {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   return sms;
 }
-inline int default_service_ctas(int worker_ctas) { return worker_ctas >= 32 ? (worker_ctas * 10 + 51) / 52 : 0; }
+inline int default_service_ctas(int worker_ctas) { return worker_ctas >= 32 ? (worker_ctas * 10 + 32) / 64 : 0; }
 inline void device_fill(int& replicas, int& service) {
   const int sms = sm_count();
   int w = sms;

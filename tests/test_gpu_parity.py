@@ -9,7 +9,7 @@ import pytest
 from conftest import compare_engines
 from oracle.binding import OracleDMD
 from parallel_dmd_for_biomolecules_b200 import genconfig, tables
-from parallel_dmd_for_biomolecules_b200.dmd import DMD, DMDError
+from parallel_dmd_for_biomolecules_b200.dmd import DMD, DMDError, device_fill
 
 pytestmark = pytest.mark.gpu
 
@@ -154,12 +154,51 @@ def test_retemp_and_distinct_states(tab, system_b):
         compare_engines(o, dev2, replica=r, n_events=5000 if r == 1 else 0)
 
 
+@pytest.mark.parametrize("which,canon,tstar,n_events", [("B", True, 0.18, 100000), ("A", True, 0.5, 60000), ("H", True, 0.10, 300000)])
+def test_list_rebuild_service_does_not_change_results(tab, system_a, system_b, which, canon, tstar, n_events):
+    """Engine 1 with list-rebuild service CTAs (nbor() + events() done by other CTAs of the event-loop kernel, on
+    other SMs) against the oracle, and against the same run with every warp rebuilding its own lists: identical
+    committed-event sequences, times, final state and tallies -- also when the lists are rebuilt many times and
+    H-bonds form (H: the 8 x A12 box at T* = 0.10)."""
+    if which == "H":
+        topo, sv = genconfig.generate_box(["AAAAAAAAAAAA"], [8], 45.0, 0.10, tab, seed=1)
+        boxl = 45.0
+    else:
+        topo, sv, boxl = system_a if which == "A" else system_b
+    p = tables.make_params(boxl=boxl, tstar=tstar, canon=canon, n_replicas=3, log_capacity=n_events, engine=1, seed=7)
+    ora, dev = _pair(p, topo, tab, sv)
+    dev.set_service_ctas(3)
+    compare_engines(ora, dev, replica=0, n_events=n_events)
+    assert dev.stats(0).updates + dev.stats(0).forced_updates >= 10  # the lists were rebuilt by the service
+    ref = DMD(p, topo, tab)
+    ref.set_state(sv)
+    ref.set_service_ctas(0)
+    ref.run(n_events)
+    for r in range(3):
+        a, b = dev.event_log(r), ref.event_log(r)
+        for f in ("i", "j", "type", "t"):
+            assert np.array_equal(a[f], b[f]), (r, f)
+        assert np.array_equal(dev.state(r)["sv"], ref.state(r)["sv"])
+        assert np.array_equal(dev.calendar(r)[0], ref.calendar(r)[0])
+    with pytest.raises(DMDError):
+        dev.set_service_ctas(-2)
+
+
+def test_device_fill_matches_the_launch(tab):
+    replicas, service = device_fill(0)
+    assert replicas > 0 and replicas % 28 == 0 and service >= 0
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    assert replicas // 28 + service <= sms
+
+
 def test_full_size_properties(tab, system_b):
-    """BASELINE config 2 at bench size: 4144 replicas of the 48-peptide box.  Size-independent properties:
+    """BASELINE config 2 at bench size: the replica count that fills the device (dmdb_device_fill: 3584 replicas of the
+    48-peptide box on a 148-SM B200, next to 20 list-rebuild service CTAs).  Size-independent properties:
     NVE energy is conserved in every replica, every replica's final state passes checkover.f (sampled), identical
     replicas stay bit-identical, and a second run of the same handle state is deterministic."""
     topo, sv, boxl = system_b
-    R = 4144
+    R = device_fill(0)[0]
     p = tables.make_params(boxl=boxl, tstar=0.18, canon=False, n_replicas=R)
     dev = DMD(p, topo, tab)
     dev.set_state(sv)

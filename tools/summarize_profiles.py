@@ -15,7 +15,10 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__inst_executed.sum,", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sass__inst_executed_register_spilling",
         "smsp__average_warps_issue_stalled", "smsp__average_warp_latency_per_inst_issued",
-        "sm__throughput.avg.pct", "sm__cycles_elapsed.max ", "lts__t_sectors_srcunit_tex_op_read.sum "]
+        "sm__throughput.avg.pct", "sm__cycles_elapsed.max ", "lts__t_sectors_srcunit_tex_op_read.sum ",
+        # instruction supply: SM instruction cache (32 KB) hit rate and the GPC-level cache behind it
+        "sm__icc_request_hit_rate", "sm__icc_requests.sum", "gcc__cache_requests_type_instruction",
+        "l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate", "l1tex__t_requests_pipe_lsu_mem_local_op"]
 
 
 def launches(tag, path):
@@ -50,8 +53,8 @@ def raw(tag, rep, kern):
                 if any(h.startswith(k.strip(" ,")) for k in KEYS):
                     f.write("%-90s %-12s %s\n" % (h, u, v))
     print(open(out).read()[:6000])
-    lines = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep,
-                            os.path.join(ROOT, "parallel_dmd_for_biomolecules_b200", "libdmdb200.so"), kern],
+    lib = os.environ.get("DMDB_LIB") or os.path.join(ROOT, "parallel_dmd_for_biomolecules_b200", "libdmdb200.so")  # the profiled build
+    lines = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, lib, kern],
                            capture_output=True, text=True).stdout
     with open(os.path.join(ROOT, "profiles", tag + "_ncu_lines.txt"), "w") as f:
         f.write("# per-source-line / per-function executed warp instructions and stall samples (tools/ncu_lines.py)\n")
