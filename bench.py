@@ -355,7 +355,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "dmd_event_loop_kernel",
                          "algorithmic_bytes_per_launch": abytes / args.steps,
-                         "note": "latency/issue-bound gather workload: see DESIGN.md 'Roofline'"},
+                         "note": "bound by instruction supply (32 KB SM instruction cache) and dependent-gather latency, not by HBM: see DESIGN.md section 4"},
         }
         if world == 1 and not args.no_extras:
             d.close()

@@ -280,7 +280,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, DMD_MIN_CTAS) dmd_event_lo
   const int rid = r0 + w;
   Rep r;
   rep_bind(r, d, tab, sm.cq[threadIdx.x >> 5], rid);
-  if (n_srv > 0) r.svc = d.svc_flag + rid;
+  if (n_srv > 0) {
+    r.svc = d.svc_flag + rid;
+    r.svc_ctl = d.svc_ctl;
+  }
   if (r.error == 0) run_events(r, n_events, (flags & 1) != 0);
   rep_save(r);
   if (n_srv > 0 && Warp::lane() == 0) atomicAdd(&d.svc_ctl[0], 1ull);  // the service CTAs leave when all warps are done
@@ -972,8 +975,20 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
         const int sms = sm_count();
         const int asked = ((flags >> 8) & 0xffff) - 1;  // dmdb_set_service_ctas; -1 = automatic
         const char* sv = getenv("DMDB_SVC");          // tuning override
-        const int want = sv ? atoi(sv) : (asked >= 0 ? asked : default_service_ctas(grid));
-        n_srv = want < sms - grid ? want : sms - grid;
+        if (sv || asked >= 0) {
+          const int want = sv ? atoi(sv) : asked;
+          n_srv = want < sms - 1 ? want : sms - 1;
+        } else if (grid <= sms) {  // one wave: as many service CTAs as fit beside the event-loop CTAs
+          const int want = default_service_ctas(grid);
+          n_srv = want < sms - grid ? want : sms - grid;
+          if (3 * n_srv < want) n_srv = 0;  // too few would only make the warps wait (measured: 4 of 22 is a loss)
+        } else {  // several waves: event-loop CTAs take turns on the SMs the service CTAs leave free, if that is faster
+          int w = sms, srv = 0;
+          device_fill(w, srv);
+          w /= WARPS_PER_CTA;
+          // per event-loop SM: 1.37e6 events/s with the service, 0.93e6 without
+          if (srv > 0 && ((grid + w - 1) / w) / 1.37 < ((grid + sms - 1) / sms) / 0.93) n_srv = srv;
+        }
         if (n_srv < 0) n_srv = 0;
       }
       flags &= 0xff;
@@ -1006,8 +1021,9 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
         if (getenv("DMDB_DEBUG")) {
           unsigned long long ctl[SVC_CTL_WORDS];
           d2h(ctl, d.svc_ctl, sizeof(ctl));
-          fprintf(stderr, "service: %d CTAs, %llu worker warps done, %llu rebuilds served, %.1f us each, %.1f ms busy per CTA\n", n_srv,
-                  ctl[0], ctl[1], ctl[1] ? (double)ctl[4] / ctl[1] / 1.9e3 : 0.0, (double)ctl[4] / n_srv / 1.9e6);
+          fprintf(stderr, "service: %d CTAs, %llu worker warps done, %llu rebuilds served, %.1f us each, %.1f ms busy per CTA; "
+                  "%llu requests taken back, mean wait %.1f us\n", n_srv, ctl[0], ctl[1], ctl[1] ? (double)ctl[4] / ctl[1] / 1.9e3 : 0.0,
+                  (double)ctl[4] / n_srv / 1.9e6, ctl[2], ctl[1] + ctl[2] ? (double)ctl[3] / (ctl[1] + ctl[2]) / 1.9e3 : 0.0);
         }
       }
       break;

@@ -47,6 +47,7 @@ struct Rep {
   OutRec* out;
   int32_t* cq;  // cascade queue storage (shared memory on the device)
   int32_t* svc;  // this replica's request word of the list-rebuild service, or nullptr: rebuild in place
+  unsigned long long* svc_ctl;  // service counters ([2] requests taken back, [3] cycles spent waiting)
   // scalars cached in registers (identical in every lane)
   double t, tfalse, old_tfalse, setemp, interval, t_fact, interval_max, n_forced, avegtime;
   int64_t coll;
@@ -111,6 +112,7 @@ DMD_DEV void rep_bind(Rep& r, const DevArrays& d, const Staged& st, int32_t* cq,
   r.out = d.out + rr * d.out_cap;
   r.cq = cq;
   r.svc = nullptr;
+  r.svc_ctl = nullptr;
   r.dirty0 = r.dirty1 = 0;
   rep_load_scalars(r);
 }
@@ -1107,6 +1109,10 @@ DMD_COLD bool svc_request(Rep r) {
         break;
       }
       __nanosleep(1500);
+    }
+    if (r.svc_ctl) {
+      if (res == 1) atomicAdd(&r.svc_ctl[2], 1ull);
+      atomicAdd(&r.svc_ctl[3], (unsigned long long)(clock64() - t0));
     }
   }
   res = Warp::shfl(res, 0);
