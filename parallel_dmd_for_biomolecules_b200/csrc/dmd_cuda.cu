@@ -81,120 +81,9 @@ __device__ __forceinline__ int replica_of_warp(int r0, int nrep) {
   return w < nrep ? r0 + w : -1;
 }
 
-// ---- list-rebuild service.  dmd_rebuild_service_kernel runs beside the event loop (second stream, its own SMs)
-// and serves the rebuild requests of the worker warps (svc_request in dmd_engine.h) with all threads of a CTA --
-// cell_add.f + nbor.f + events.f for one replica at a time, the same functions the CTA-per-replica engine uses --
-// until every worker warp has finished.  The replica's bead records and the cell grid (coarse list heads, chain
-// links, packed cell coordinates) are staged in shared memory when they fit, so that the walk over the stencil and
-// the distance tests cost shared-memory round trips instead of L2/DRAM ones.
-#ifndef DMD_SVC_THREADS
-#define DMD_SVC_THREADS 1024
-#endif
-constexpr int SVC_THREADS = DMD_SVC_THREADS;
-struct SvcLayout {
-  size_t heads, cnext, cpk, rec, total;
-  bool grid, rec_fits;
-};
-__host__ __device__ inline SvcLayout svc_layout(int N, int ncc3, size_t limit) {
-  SvcLayout L;
-  size_t off = (sizeof(SmemConsts) + 127) & ~(size_t)127;
-  L.total = off;
-  L.heads = off; off += (((size_t)ncc3 * 4) + 127) & ~(size_t)127;
-  L.cnext = off; off += (((size_t)N * 4) + 127) & ~(size_t)127;
-  L.cpk = off; off += (((size_t)N * 4) + 127) & ~(size_t)127;
-  L.grid = off <= limit;
-  if (L.grid) L.total = off;
-  L.rec = off; off += (size_t)N * sizeof(BeadRec);
-  L.rec_fits = L.grid && off <= limit;
-  if (L.rec_fits) L.total = off;
-  return L;
-}
-
-__global__ void __launch_bounds__(SVC_THREADS, 1) dmd_rebuild_service_kernel(DevArrays d, int r0, int nrep, unsigned smem_limit) {
-  extern __shared__ __align__(128) unsigned char svc_smem[];
-  __shared__ int s_pick, s_state;
-  SmemConsts* sconst = reinterpret_cast<SmemConsts*>(svc_smem);
-  const Staged tab = stage_consts(d, sconst);
-  const SvcLayout L = svc_layout(d.n_beads, d.ncc3, smem_limit);
-  int32_t* const s_heads = reinterpret_cast<int32_t*>(svc_smem + L.heads);
-  int32_t* const s_cnext = reinterpret_cast<int32_t*>(svc_smem + L.cnext);
-  uint32_t* const s_cpk = reinterpret_cast<uint32_t*>(svc_smem + L.cpk);
-  BeadRec* const s_rec = reinterpret_cast<BeadRec*>(svc_smem + L.rec);
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int scan0 = (int)(((long long)blockIdx.x * nrep) / (int)gridDim.x);  // the CTAs start their scans at different places
-  const long long t_start = clock64();
-  long long t_last = t_start;  // thread 0: last time there was something to do
-  while (true) {
-    if (tid == 0) s_pick = 0x7fffffff;
-    __syncthreads();
-    for (int k = tid; k < nrep; k += nt) {
-      int idx = k + scan0;
-      if (idx >= nrep) idx -= nrep;
-      if (*(volatile int32_t*)(d.svc_flag + r0 + idx) == 1) {
-        atomicMin(&s_pick, idx);
-        break;
-      }
-    }
-    __syncthreads();
-    const int pick = s_pick;
-    if (tid == 0) {
-      if (pick == 0x7fffffff) {
-        const unsigned long long done = *(volatile unsigned long long*)&d.svc_ctl[0];
-        s_state = done >= (unsigned long long)nrep ? 2 : 0;
-        // kernels of two streams are not guaranteed to run side by side: leave when the event loop has not shown up
-        // after ~40 ms (it may be queued BEHIND this kernel), or when nothing has been asked for ~2 s
-        const long long now = clock64();
-        const bool alive = *(volatile unsigned long long*)&d.svc_ctl[5] != 0ull;
-        if ((!alive && now - t_start > 80000000ll) || now - t_last > 4000000000ll) s_state = 2;
-        if (s_state == 0) __nanosleep(1000);
-      } else {
-        t_last = clock64();
-        s_state = svc_cas_acq_rel(d.svc_flag + r0 + pick, 1, 2) == 1 ? 1 : 0;
-      }
-    }
-    __syncthreads();
-    const int state = s_state;
-    if (state == 2) return;
-    if (state == 0) continue;
-    const long long t0 = clock64();
-    const int rid = r0 + pick;
-    Rep q;
-    rep_bind(q, d, tab, nullptr, rid);  // scalars as saved by the requesting warp (tfalse = 0, new interval_max)
-    q.error = 0;
-    if (L.grid) {
-      for (int k = tid; k < d.ncc3; k += nt) s_heads[k] = -1;
-      q.cellhead = s_heads;
-      q.cnext = s_cnext;
-      q.cpk = s_cpk;
-    }
-    if (L.rec_fits) {
-      const uint4* src = reinterpret_cast<const uint4*>(q.rec);
-      uint4* dst = reinterpret_cast<uint4*>(s_rec);
-      for (int k = tid; k < q.N * 4; k += nt) dst[k] = src[k];
-      q.rec = s_rec;
-    }
-    __syncthreads();
-    cell_build(q, tid, nt);
-    __syncthreads();
-    nbor_build(q, tid, nt);
-    if (!L.grid) {
-      __syncthreads();
-      cell_clear(q, tid, nt);
-    }
-    for (int l = tid; l < q.N; l += nt) redo_lane(q, l);  // events.f:23-107; the requester refreshes the group minima
-    if (q.error && Warp::lane() == 0 && atomicCAS(&q.sc->error, 0, q.error) == 0) q.sc->error_info = q.error_info;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-      svc_st_release(d.svc_flag + rid, 0);
-      atomicAdd(&d.svc_ctl[4], (unsigned long long)(clock64() - t0));
-      atomicAdd(&d.svc_ctl[1], 1ull);
-    }
-  }
-}
-
-// The same service as a ROLE of the event-loop kernel (its first n_in CTAs): no second stream, so nothing depends on
-// two kernels running side by side.  The cell grid of the rebuild aliases the CTA's static shared memory (tables +
+// ---- list-rebuild service (svc_request in dmd_engine.h is the requesting side).
+// A ROLE of the event-loop kernel (its first n_srv CTAs): one kernel, so nothing depends on two kernels running side
+// by side (a second-stream service kernel with its own shared memory measured the same and was dropped).  The cell grid of the rebuild aliases the CTA's static shared memory (tables +
 // cascade queues, which a service CTA does not use); bead records and tables are read through L1/L2.
 struct alignas(16) EvlSmem {
   SmemConsts consts;
@@ -266,16 +155,15 @@ __device__ __noinline__ void svc_serve_in_kernel(DevArrays d, int r0, int nrep, 
   }
 }
 
-// n_srv: service CTAs exist (this kernel's first n_in CTAs, or dmd_rebuild_service_kernel on a second stream)
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, DMD_MIN_CTAS) dmd_event_loop_kernel(DevArrays d, int r0, int nrep, long long n_events, int flags, int n_srv, int n_in) {
+// the first n_srv CTAs are the list-rebuild service, the others run the event loop
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, DMD_MIN_CTAS) dmd_event_loop_kernel(DevArrays d, int r0, int nrep, long long n_events, int flags, int n_srv) {
   __shared__ EvlSmem sm;
-  if ((int)blockIdx.x < n_in) {
+  if ((int)blockIdx.x < n_srv) {
     svc_serve_in_kernel(d, r0, nrep, reinterpret_cast<unsigned char*>(&sm), sizeof(EvlSmem));
     return;
   }
   const Staged tab = stage_consts(d, &sm.consts);
-  if (n_srv > 0 && threadIdx.x == 0) *(volatile unsigned long long*)&d.svc_ctl[5] = 1ull;  // the event loop is running
-  const int w = ((int)blockIdx.x - n_in) * WARPS_PER_CTA + (threadIdx.x >> 5);
+  const int w = ((int)blockIdx.x - n_srv) * WARPS_PER_CTA + (threadIdx.x >> 5);
   if (w >= nrep) return;
   const int rid = r0 + w;
   Rep r;
@@ -735,8 +623,6 @@ namespace be {
 
 static cudaStream_t g_stream = nullptr;
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
-static cudaStream_t g_stream2 = nullptr;  // the list-rebuild service runs beside the event loop
-static cudaEvent_t g_evs0 = nullptr, g_evs1 = nullptr;
 
 inline bool init(int device, std::string& err) {
   int n = 0;
@@ -935,7 +821,7 @@ inline int run_grid(const dmd::DevArrays& d, int r0, int nrep, long long n_event
       } else if (hdr.status == 1 && !sc.error && sc.coll < target) {  // one calendar entry for the serial engine
         dmd_bulk_groups_kernel<<<dim3((d.cal_stride / 32 + BULK_THREADS / 32 - 1) / (BULK_THREADS / 32), 1), BULK_THREADS, 0, g_stream>>>(d, rid);
         const auto tc0 = std::chrono::steady_clock::now();
-        dmd_event_loop_kernel<<<1, WARPS_PER_CTA * 32, 0, g_stream>>>(d, rid, 1, 1, 0, 0, 0);
+        dmd_event_loop_kernel<<<1, WARPS_PER_CTA * 32, 0, g_stream>>>(d, rid, 1, 1, 0, 0);
         launches += 2;
         CUDA_OK(cudaGetLastError());
         d2h(&sc, d.scal + rid, sizeof(sc));
@@ -969,7 +855,7 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
         if (const char* cv = getenv("DMDB_CARVEOUT"))
           CUDA_OK(cudaFuncSetAttribute(dmd_event_loop_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
       }
-      // service CTAs (dmd_rebuild_service_kernel): only when they and every worker CTA can be resident at once
+      // list-rebuild service CTAs (svc_serve_in_kernel)
       int n_srv = 0;
       {
         const int sms = sm_count();
@@ -992,39 +878,14 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
         if (n_srv < 0) n_srv = 0;
       }
       flags &= 0xff;
-      const char* svm = getenv("DMDB_SVC_MODE");
-      const bool two_kernels = svm && atoi(svm) == 2;
-      if (n_srv > 0 && !two_kernels) CUDA_OK(cudaMemsetAsync(d.svc_ctl, 0, SVC_CTL_WORDS * 8, g_stream));
-      if (n_srv > 0 && two_kernels) {
-        if (!g_stream2) {
-          CUDA_OK(cudaStreamCreateWithFlags(&g_stream2, cudaStreamNonBlocking));
-          CUDA_OK(cudaEventCreateWithFlags(&g_evs0, cudaEventDisableTiming));
-          CUDA_OK(cudaEventCreateWithFlags(&g_evs1, cudaEventDisableTiming));
-        }
-        const size_t svc_limit = smem_optin() - 1024;  // minus the kernel's static shared memory
-        const SvcLayout L = svc_layout(d.n_beads, d.ncc3, svc_limit);
-        CUDA_OK(cudaFuncSetAttribute(dmd_rebuild_service_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-        CUDA_OK(cudaMemsetAsync(d.svc_ctl, 0, SVC_CTL_WORDS * 8, g_stream));
-        CUDA_OK(cudaEventRecord(g_evs0, g_stream));          // the service starts after everything queued so far ...
-        CUDA_OK(cudaStreamWaitEvent(g_stream2, g_evs0, 0));
-        dmd_rebuild_service_kernel<<<n_srv, SVC_THREADS, L.total, g_stream2>>>(d, r0, nrep, (unsigned)svc_limit);
-        CUDA_OK(cudaGetLastError());
-        CUDA_OK(cudaEventRecord(g_evs1, g_stream2));
-      }
-      const int n_in = two_kernels ? 0 : n_srv;
-      dmd_event_loop_kernel<<<grid + n_in, block, 0, g_stream>>>(d, r0, nrep, arg, flags, n_srv, n_in);
-      if (n_srv > 0) {
-        if (two_kernels) {
-          CUDA_OK(cudaStreamWaitEvent(g_stream, g_evs1, 0));   // ... and the step ends when it has left
-          nl = 2;
-        }
-        if (getenv("DMDB_DEBUG")) {
-          unsigned long long ctl[SVC_CTL_WORDS];
-          d2h(ctl, d.svc_ctl, sizeof(ctl));
-          fprintf(stderr, "service: %d CTAs, %llu worker warps done, %llu rebuilds served, %.1f us each, %.1f ms busy per CTA; "
-                  "%llu requests taken back, mean wait %.1f us\n", n_srv, ctl[0], ctl[1], ctl[1] ? (double)ctl[4] / ctl[1] / 1.9e3 : 0.0,
-                  (double)ctl[4] / n_srv / 1.9e6, ctl[2], ctl[1] + ctl[2] ? (double)ctl[3] / (ctl[1] + ctl[2]) / 1.9e3 : 0.0);
-        }
+      if (n_srv > 0) CUDA_OK(cudaMemsetAsync(d.svc_ctl, 0, SVC_CTL_WORDS * 8, g_stream));
+      dmd_event_loop_kernel<<<grid + n_srv, block, 0, g_stream>>>(d, r0, nrep, arg, flags, n_srv);
+      if (n_srv > 0 && getenv("DMDB_DEBUG")) {
+        unsigned long long ctl[SVC_CTL_WORDS];
+        d2h(ctl, d.svc_ctl, sizeof(ctl));
+        fprintf(stderr, "service: %d CTAs, %llu worker warps done, %llu rebuilds served, %.1f us each, %.1f ms busy per CTA; "
+                "%llu requests taken back, mean wait %.1f us\n", n_srv, ctl[0], ctl[1], ctl[1] ? (double)ctl[4] / ctl[1] / 1.9e3 : 0.0,
+                (double)ctl[4] / n_srv / 1.9e6, ctl[2], ctl[1] + ctl[2] ? (double)ctl[3] / (ctl[1] + ctl[2]) / 1.9e3 : 0.0);
       }
       break;
     }

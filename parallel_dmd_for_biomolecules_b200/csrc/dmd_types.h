@@ -187,7 +187,7 @@ struct DevArrays {
   // neighbour-list + calendar rebuilds for the warps of all other CTAs, so that the event-loop SMs keep only the
   // hot loop in their 32 KB instruction caches)
   int32_t* svc_flag;      // per replica: 0 idle, 1 rebuild requested, 2 being served, 3 taken back by its own warp
-  unsigned long long* svc_ctl;  // [0] finished worker warps [1] requests [2] served locally [3] wait cycles [4] service cycles
+  unsigned long long* svc_ctl;  // [0] finished worker warps [1] rebuilds served [2] requests taken back [3] wait cycles [4] service cycles
 };
 constexpr int SVC_CTL_WORDS = 8;
 

@@ -184,6 +184,41 @@ def test_list_rebuild_service_does_not_change_results(tab, system_a, system_b, w
         dev.set_service_ctas(-2)
 
 
+def test_config3_temperature_ladder_with_exchange(tab, system_b):
+    """BASELINE config 3 on one GPU: the reference's 11 temperatures (temp_018 ... temp_050) as two ladders of 48-peptide
+    boxes with replica exchange between the runs.  The set of temperatures of each ladder is conserved, swaps are
+    accepted, every replica's kinetic temperature follows the temperature it currently holds (Andersen thermostat),
+    hot replicas lose their order faster than cold ones, and a sampled final state passes checkover.f."""
+    from parallel_dmd_for_biomolecules_b200 import replica_exchange as rx
+    topo, sv, boxl = system_b
+    L = len(rx.LADDER)
+    R = 2 * L
+    dev = DMD(tables.make_params(boxl=boxl, tstar=0.18, canon=True, n_replicas=R, seed=5), topo, tab)
+    dev.set_state(sv)
+    dev.apply_temperatures(list(rx.LADDER) * 2)
+    swaps = 0
+    for step in range(8):
+        dev.run(30000)
+        before = dev.potential_energies()[1].copy()
+        new_t, changed = rx.exchange_step(dev, step, seed=99, ladder_size=L)
+        swaps += changed
+        for lad in range(2):
+            assert sorted(new_t[lad * L:(lad + 1) * L]) == sorted(rx.LADDER)
+        assert np.array_equal(dev.potential_energies()[1], new_t)
+        assert changed == int((new_t != before).sum())
+    assert swaps > 0
+    dev.run(60000)
+    _, tnow = dev.potential_energies()
+    tred = np.array([dev.energy(r).tred for r in range(R)])
+    assert np.all(np.abs(tred / (12.0 * tnow) - 1.0) < 0.12)  # 1344 beads: sigma of the kinetic temperature ~ 2 %
+    assert dev.stats().forced_updates >= 0 and dev.stats().events == R * (8 * 30000 + 60000)
+    dev.sync_positions()
+    hot = int(np.argmax(tnow))
+    o = OracleDMD(tables.make_params(boxl=boxl, tstar=float(tnow[hot]), canon=True), topo, tab)
+    o.set_state(dev.state(hot)["sv"], dev.state(hot)["bptnr"])
+    assert not o.checkover()[0]
+
+
 def test_device_fill_matches_the_launch(tab):
     replicas, service = device_fill(0)
     assert replicas > 0 and replicas % 28 == 0 and service >= 0
