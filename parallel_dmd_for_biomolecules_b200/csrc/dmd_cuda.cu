@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(BK_MAXW * 32, 1) dmd_block_loop_kernel(DevArra
     }
     __syncthreads();
     blk_run(S, r, claim, w, nw);
+    harvest_counters(r);
     if (w != 0 && Warp::lane() == 0) {
       blk_atomic_add64(&S.n_pair_pred, r.n_pair_pred);
       blk_atomic_add64(&S.n_nbr_visits, r.n_nbr_visits);
@@ -415,6 +416,7 @@ __global__ void __launch_bounds__(BK_MAXW * 32, 1) dmd_grid_loop_kernel(DevArray
   const int64_t pp0 = r.n_pair_pred, nv0 = r.n_nbr_visits;
   if (gw == 0) r.n_log = S->n_log;
   grid_run(*S, r, claim, gw, ngw);
+  harvest_counters(r);
   if (Warp::lane() == 0 && gw != 0) {  // work counters of the other warps
     atomicAdd((unsigned long long*)&S->nevents[30], (unsigned long long)(r.n_pair_pred - pp0));
     atomicAdd((unsigned long long*)&S->nevents[31], (unsigned long long)(r.n_nbr_visits - nv0));

@@ -60,6 +60,7 @@ static void trace_run_block(const DevArrays& d, int rid, long long n_events, int
       if (w != 0) r.n_pair_pred = r.n_nbr_visits = 0;
       blk_run(*S, r, claim.data(), w, nw);
       if (w != 0) {
+        harvest_counters(r);
         blk_atomic_add64(&S->n_pair_pred, r.n_pair_pred);
         blk_atomic_add64(&S->n_nbr_visits, r.n_nbr_visits);
       }
