@@ -150,7 +150,7 @@ DMD_DEV void rep_save(Rep& r) {
   harvest_counters(r);
   if (Warp::lane() == 0) {
     RepScalars& q = *r.sc;
-    q.t = r.t; q.tfalse = r.tfalse; q.old_tfalse = r.old_tfalse; q.setemp = r.setemp; q.interval = r.interval;
+    q.t = r.t; q.tfalse = r.tfalse; q.old_tfalse = r.tfalse; q.setemp = r.setemp; q.interval = r.interval;
     q.t_fact = r.t_fact; q.interval_max = r.interval_max; q.n_forced = r.n_forced; q.avegtime = r.avegtime;
     q.coll = r.coll; q.rng_ctr = r.ctr; q.n_pair_pred = r.n_pair_pred; q.n_nbr_visits = r.n_nbr_visits;
     q.n_log = r.n_log; q.n_out = r.n_out; q.error = r.error; q.error_info = r.error_info;
@@ -1173,7 +1173,7 @@ DMD_COLD bool svc_request(Rep r) {
 // ---- cold pseudo-events: they work on a by-value copy of the view and hand the scalars back through r.sc
 // main.F90:997-1048; returns the bead that got its new velocity -- the caller re-predicts it (:1049) with the hot
 // loop's own copy of partial_events, so that a ghost event does not drag a second copy through the instruction cache
-DMD_COLD int ghost_event_cold(Rep r) {
+DMD_COLD int ghost_event_cold(Rep r, double prev_tfalse) {
   const int N = r.N;
   int i;
   do {
@@ -1213,7 +1213,7 @@ DMD_COLD int ghost_event_cold(Rep r) {
     r.cal[N].t = tnext;
     r.sc->numghosts += 1;
   }
-  if (r.tfalse < r.old_tfalse) r.tfalse = r.old_tfalse;  // main.F90:1047
+  if (r.tfalse < prev_tfalse) r.tfalse = prev_tfalse;  // main.F90:1047 (old_tfalse = time of the previous event)
   log_event(r, N, i, -2, 0);
   rep_save(r);
   return i;
@@ -1360,6 +1360,7 @@ DMD_COLD void output_event_cold(Rep r) {
 // one iteration of main.F90:484-1258 with serial semantics
 // process calendar entry o (already popped): main.F90:639-1246
 DMD_DEV void process_one(Rep& r, int o, const CalEnt& ev) {
+  const double prev_tfalse = r.tfalse;  // old_tfalse of main.F90: between two events it equals tfalse, so it needs no register
   r.tfalse = ev.t;
   r.coll += 1;
   int pi = o, pj = ev.ptnr;  // the bead(s) whose events have to be re-predicted (partial_events.f)
@@ -1369,7 +1370,7 @@ DMD_DEV void process_one(Rep& r, int o, const CalEnt& ev) {
   } else {
     rep_save(r);  // hand the scalars to the out-of-line handler through r.sc ...
     if (o == r.N) {
-      pi = ghost_event_cold(r);
+      pi = ghost_event_cold(r, prev_tfalse);
       pj = -1;
     } else {
       redo = false;
@@ -1383,7 +1384,6 @@ DMD_DEV void process_one(Rep& r, int o, const CalEnt& ev) {
     if (redo) mark_dirty(r, r.N >> 5);  // the next ghost time
   }
   if (redo) partial_events(r, pi, pj, xpulse_del);  // main.F90:943, :1049 -- the only call site in the loop
-  r.old_tfalse = r.tfalse;
 }
 
 // returns the owner index of the processed calendar entry, or -1 on error
@@ -1402,7 +1402,8 @@ DMD_DEV int step(Rep& r) {
 // stop_at_output: return right after the output pseudo-event (main.F90:1191-1246) has been processed, so that the
 // host can write the .energy line and the .config / .bptnr / .lastvel records exactly where the reference does
 DMD_DEV void run_events(Rep& r, int64_t n_events, bool stop_at_output) {
-  for (int64_t n = 0; n < n_events; n++) {
+  const int64_t coll_end = r.coll + n_events;  // coll counts every processed calendar entry (main.F90:639)
+  while (r.coll < coll_end) {
     const int o = step(r);
     if (o < 0 || (stop_at_output && o == r.N + 2)) break;
   }
