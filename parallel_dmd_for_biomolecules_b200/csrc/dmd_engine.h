@@ -350,6 +350,29 @@ DMD_DEV void seg_argmin(double& v, int& key, unsigned mask) {
 #endif
 }
 
+// the two halves of a bead record: integer part (partners, identity, overlay codes) / positions and velocities
+DMD_DEV void rec_load_tail(BeadRec& dst, const BeadRec* src) {
+#if DMD_W > 1
+  const int4 t = *reinterpret_cast<const int4*>(reinterpret_cast<const char*>(src) + 48);
+  dst.bptnr = t.x; dst.er1 = t.y; dst.er2 = t.z;
+  dst.ident = (uint8_t)(t.w & 0xff); dst.ov1 = (uint8_t)((t.w >> 8) & 0xff); dst.ov2 = (uint8_t)((t.w >> 16) & 0xff);
+  dst.pad = 0;
+#else
+  dst.bptnr = src->bptnr; dst.er1 = src->er1; dst.er2 = src->er2;
+  dst.ident = src->ident; dst.ov1 = src->ov1; dst.ov2 = src->ov2; dst.pad = 0;
+#endif
+}
+DMD_DEV void rec_load_head(BeadRec& dst, const BeadRec* src) {
+#if DMD_W > 1
+  asm volatile("" ::: "memory");  // a load the compiler must not hoist out of the caller's loop
+  const double2* p = reinterpret_cast<const double2*>(src);
+  const double2 p0 = p[0], p1 = p[1], p2 = p[2];
+  dst.x = p0.x; dst.y = p0.y; dst.z = p1.x; dst.vx = p1.y; dst.vy = p2.x; dst.vz = p2.y;
+#else
+  dst.x = src->x; dst.y = src->y; dst.z = src->z; dst.vx = src->vx; dst.vy = src->vy; dst.vz = src->vz;
+#endif
+}
+
 // ONE pass = ONE copy of the prediction code in the hot loop (the loop must stay resident in the instruction
 // cache while every warp of the SM sits at a different program counter).  The warp is split into G = 1, 2 or 4
 // segments of SEG lanes; segment g handles bead beads[g]:
@@ -379,7 +402,11 @@ DMD_DEV void segmented_pass(Rep& r, int a, bool act, int sh, bool with_down, int
     if (with_down) ed0 = dnl[pl];
   }
 #endif
-  const BeadRec ra = r.rec[a];
+  // of the bead's own record only the integer part (partners, identity, overlay) is held across the pass; positions
+  // and velocities are fetched again (L1) where the geometry is formed, so that they do not occupy twelve registers
+  // while the partners' records are in flight and the predictor runs
+  BeadRec ra;
+  rec_load_tail(ra, &r.rec[a]);
   const uint32_t ma = r.c.meta[a];
   const int nu = act ? (lr ? lr->nu : (int)r.nup[a]) : -3;
   const int nd = with_down ? (lr ? lr->nd : (int)r.ndn[a]) : 0;
@@ -441,8 +468,9 @@ DMD_DEV void segmented_pass(Rep& r, int a, bool act, int sh, bool with_down, int
     CalEnt eb;
     eb.t = 0.0; eb.ptnr = -1; eb.type = -1;
     if (b >= 0) {
-      // level-2 loads, all depending on b only
+      // level-2 loads, all depending on b only (+ the position / velocity part of a's own record)
       const BeadRec rb = r.rec[b];
+      rec_load_head(ra, &r.rec[a]);
       uint32_t mlo = ma;
       if (!full) {
         eb = r.cal[b];
