@@ -226,20 +226,17 @@ DMD_DEV void flush_dirty(Rep& r) {
   Warp::sync();
 }
 
-// every lane may have changed the entry of a different bead l (l < 0: none): record the groups uniformly
+// every lane may have changed the entry of a different bead l (l < 0: none): each such lane sets the bit of its
+// group in the warp's shared-memory masks (a 32-bit shared-memory atomic; only the lanes that changed something
+// take part), groups >= 128 (very large systems) are refreshed at once
 DMD_DEV void mark_dirty_lanes(Rep& r, int l) {
   const int g = l >> 5;  // negative when l < 0
-  unsigned a0 = (g >= 0 && g < 32) ? 1u << g : 0u;
-  unsigned a1 = (g >= 32 && g < 64) ? 1u << (g - 32) : 0u;
-  a0 = warp_or(a0);
-  a1 = warp_or(a1);
-  if (Warp::lane() == 0) warp_dirty(r)[0] |= (uint64_t)a0 | ((uint64_t)a1 << 32);
-  if (r.G > 64) {  // larger systems (uniform branch)
-    unsigned b0 = (g >= 64 && g < 96) ? 1u << (g - 64) : 0u;
-    unsigned b1 = (g >= 96 && g < 128) ? 1u << (g - 96) : 0u;
-    b0 = warp_or(b0);
-    b1 = warp_or(b1);
-    if (Warp::lane() == 0) warp_dirty(r)[1] |= (uint64_t)b0 | ((uint64_t)b1 << 32);
+#if DMD_W > 1
+  if (g >= 0 && g < 128) atomicOr(reinterpret_cast<unsigned*>(warp_dirty(r)) + (g >> 5), 1u << (g & 31));
+#else
+  if (g >= 0 && g < 128) warp_dirty(r)[g >> 6] |= 1ull << (g & 63);
+#endif
+  if (r.G > 128) {  // uniform branch
     unsigned m = Warp::ballot(g >= 128);
     while (m) {
       int src = dmd_ffs(m) - 1;
