@@ -45,7 +45,7 @@ struct Rep {
   double* oldr;
   int32_t *cellhead, *cnext, *cellof;
   uint32_t* cpk;  // packed fine cell coordinates of each bead (10 bits per dimension)
-  double* tmin1;
+  unsigned long long* tmin1;  // per-group minima as ordered images (ord_bits64): lowered with an integer atomicMin
   RepScalars* sc;
   EventLogRec* log;
   OutRec* out;
@@ -129,7 +129,7 @@ DMD_DEV void rep_bind(Rep& r, const DevArrays& d, const Staged& st, int32_t* cq,
   r.cpk = d.cpk + rr * N;
   r.cnext = d.cnext + rr * N;
   r.cellof = d.cellof + rr * N;
-  r.tmin1 = d.tmin1 + rr * d.ngroups;
+  r.tmin1 = reinterpret_cast<unsigned long long*>(d.tmin1) + rr * d.ngroups;
   r.sc = d.scal + rr;
   r.log = d.log + rr * (d.log_cap > 0 ? d.log_cap : 1);
   r.out = d.out + rr * d.out_cap;
@@ -177,7 +177,7 @@ DMD_DEV void group_min_update(Rep& r, int g) {
     if (x < v) v = x;
   }
   v = warp_min(v);
-  if (Warp::lane() == 0) r.tmin1[g] = v;
+  if (Warp::lane() == 0) r.tmin1[g] = ord_bits64(v);
 }
 
 DMD_DEV void mark_dirty(Rep& r, int g) {  // g warp-uniform
@@ -215,8 +215,8 @@ DMD_DEV void flush_dirty(Rep& r) {
     x0 = warp_min(x0);
     if (g1 >= 0) x1 = warp_min(x1);
     if (Warp::lane() == 0) {
-      r.tmin1[g0] = x0;
-      if (g1 >= 0) r.tmin1[g1] = x1;
+      r.tmin1[g0] = ord_bits64(x0);
+      if (g1 >= 0) r.tmin1[g1] = ord_bits64(x1);
     }
   }
 #else
@@ -255,17 +255,17 @@ DMD_DEV void rebuild_all_groups(Rep& r) {
 
 // returns the owner index of the earliest entry (or -1) and the entry itself
 DMD_DEV int pop_min(Rep& r, CalEnt& ev) {
-  double best = T_PAD;
+  unsigned long long best = ord_bits64(T_PAD);
   int bg = 0x7fffffff;
   for (int g = Warp::lane(); g < r.G; g += DMD_W) {
-    double v = r.tmin1[g];
+    const unsigned long long v = r.tmin1[g];
     if (v < best) {  // ascending g: the first minimum keeps the lowest group
       best = v;
       bg = g;
     }
   }
-  warp_argmin(best, bg);
-  if (bg == 0x7fffffff || !(best < 1e299)) return -1;
+  warp_argmin_ord(best, bg);
+  if (bg == 0x7fffffff || !(ord_value64(best) < 1e299)) return -1;
   double v = T_PAD;
   int key = 0x7fffffff, pt = -1, ty = -1;
   for (int q = Warp::lane(); q < 32; q += DMD_W) {
@@ -462,6 +462,7 @@ DMD_DEV void segmented_pass(Rep& r, int a, bool act, int sh, bool with_down, int
     }
     bool need_full = false;
     int changed = -1;
+    double lowered_t = 0.0;
     CalEnt eb;
     eb.t = 0.0; eb.ptnr = -1; eb.type = -1;
     if (b >= 0) {
@@ -503,6 +504,7 @@ DMD_DEV void segmented_pass(Rep& r, int a, bool act, int sh, bool with_down, int
             ne.type = pack_type(type, sc);
             r.cal[b] = ne;
             changed = b;
+            lowered_t = tij;
             if (BLK && tij < u->newmin) u->newmin = tij;
           }
         }
@@ -519,8 +521,14 @@ DMD_DEV void segmented_pass(Rep& r, int a, bool act, int sh, bool with_down, int
           }
           u->n += dmd_popc(mc);
         }
-      } else {
-        mark_dirty_lanes(r, changed);
+      } else if (changed >= 0) {
+        // an entry that was only LOWERED: the group minimum follows with an integer atomicMin on its ordered image
+        // (exact -- no rescan of the group's 32 entries); entries that may rise (the writer below) mark the group
+#if DMD_W > 1
+        atomicMin(&r.tmin1[changed >> 5], ord_bits64(lowered_t));
+#else
+        if (ord_bits64(lowered_t) < r.tmin1[changed >> 5]) r.tmin1[changed >> 5] = ord_bits64(lowered_t);
+#endif
       }
       const unsigned m = Warp::ballot(need_full);
       if (m) {
@@ -911,7 +919,13 @@ DMD_DEV bool pair_event(Rep& r, int i, const CalEnt& ev) {
     xpulse_del = cr.xpulse != 0;
     r.ctr = cr.ctr;
   }
-  if (Warp::lane() == 0 && ct >= 0 && ct < 32) r.sc->nevents[ct] += 1;  // main.F90:926
+  if (Warp::lane() == 0 && ct >= 0 && ct < 32) {  // main.F90:926 (a reduction without return value: nothing to wait for)
+#if DMD_W > 1
+    atomicAdd(reinterpret_cast<unsigned long long*>(&r.sc->nevents[ct]), 1ull);
+#else
+    r.sc->nevents[ct] += 1;
+#endif
+  }
   log_event(r, i, j, ct, code);
   return xpulse_del;
 }

@@ -95,6 +95,28 @@ DMD_DEV double ord_join(unsigned hi, unsigned lo) {
   return dmd_hi_lo((int)~hi, ~lo);
 }
 
+// the same image as one 64-bit word (unsigned order == numeric order) and back
+DMD_DEV unsigned long long ord_bits64(double v) {
+  unsigned hi, lo;
+  ord_split(v, hi, lo);
+  return ((unsigned long long)hi << 32) | lo;
+}
+DMD_DEV double ord_value64(unsigned long long b) { return ord_join((unsigned)(b >> 32), (unsigned)b); }
+
+// (ordered image, key) arg-min over the warp: smallest value, ties -> smallest key; all lanes get the result
+DMD_DEV void warp_argmin_ord(unsigned long long& v, int& key) {
+#if DMD_W > 1
+  const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+  const bool c1 = hi == mhi;
+  const unsigned mlo = __reduce_min_sync(0xffffffffu, c1 ? lo : 0xffffffffu);
+  const bool c2 = c1 && lo == mlo;
+  const unsigned mkey = __reduce_min_sync(0xffffffffu, c2 ? (unsigned)key : 0xffffffffu);
+  v = ((unsigned long long)mhi << 32) | mlo;
+  key = (int)mkey;
+#endif
+}
+
 // (value, key) lexicographic arg-min over the warp: smallest value, ties -> smallest key (key >= 0).
 // All lanes get the result.  Three REDUX.MIN instructions on the device instead of a 5-round shuffle tree.
 DMD_DEV void warp_argmin(double& v, int& key) {
