@@ -219,6 +219,28 @@ def test_config3_temperature_ladder_with_exchange(tab, system_b):
     assert not o.checkover()[0]
 
 
+def test_more_replicas_than_one_wave(tab, system_b):
+    """Twice the replicas that fill the device: the event-loop CTAs take turns on the SMs the list-rebuild service CTAs
+    leave free (several waves of one kernel).  NVE replicas started from one snapshot must stay bit-identical to
+    each other and to a small handle that rebuilds its lists in place."""
+    topo, sv, boxl = system_b
+    R = 2 * device_fill(0)[0]
+    n = 6000
+    big = DMD(tables.make_params(boxl=boxl, tstar=0.18, canon=False, n_replicas=R, engine=1), topo, tab)
+    big.set_state(sv)
+    st = big.run(n)
+    assert st.events == R * n
+    small = DMD(tables.make_params(boxl=boxl, tstar=0.18, canon=False, n_replicas=2, engine=1), topo, tab)
+    small.set_state(sv)
+    small.set_service_ctas(0)
+    small.run(n)
+    assert small.stats(0).updates + small.stats(0).forced_updates >= 1  # the window contains list rebuilds
+    ref = small.state(0)["sv"]
+    for r in (0, 1, R // 2 - 1, R // 2, R - 29, R - 1):
+        assert np.array_equal(big.state(r)["sv"], ref), r
+        assert np.array_equal(big.calendar(r)[0], small.calendar(0)[0]), r
+
+
 def test_device_fill_matches_the_launch(tab):
     replicas, service = device_fill(0)
     assert replicas > 0 and replicas % 28 == 0 and service >= 0
