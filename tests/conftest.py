@@ -96,3 +96,25 @@ def check_run_until_output(tab, engines, lib_path=None):
             assert d.state(0)["coll"] == st["coll"] + 1000
     assert all(s == stops[0] for s in stops)
     return stops[0]
+
+
+def frozen_events(which):
+    """the oracle's first 10^4 NVE events of system A / B, frozen by tests/golden/make_event_fixtures.py"""
+    return np.load(os.path.join(GOLDEN, "events_system%s_nve.npz" % which))
+
+
+def check_against_frozen_events(engine_obj, fx, replica=None):
+    """engine_obj: an OracleDMD or DMD with the fixture's snapshot loaded and a log of >= 10^4 events"""
+    kw = {} if replica is None else {"replica": replica}
+    tim, nptnr, coltype = engine_obj.calendar(**kw) if kw else engine_obj.calendar()
+    assert np.array_equal(nptnr, fx["cal_ptnr0"]) and np.array_equal(coltype, fx["cal_type0"])
+    assert np.array_equal(tim, fx["cal_t0"])  # bit-equal (the bar is 1e-12 relative)
+    n = len(fx["t"])
+    engine_obj.run(n)
+    log = engine_obj.event_log(**kw) if kw else engine_obj.event_log()
+    assert len(log) == n
+    for f in ("i", "j", "type", "evcode"):
+        bad = np.nonzero(log[f] != fx[f])[0]
+        assert bad.size == 0, "frozen event sequence differs in %s at event %d" % (f, bad[0])
+    np.testing.assert_allclose(log["t"], fx["t"], rtol=1e-12, atol=0)
+    assert np.array_equal(log["t"], fx["t"])

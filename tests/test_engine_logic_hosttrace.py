@@ -151,3 +151,17 @@ def test_box_too_small_and_bad_bptnr_are_errors(tab, hosttrace_lib):
     with pytest.raises(DMDError) as e:
         d.set_state(sv, bad)
     assert e.value.code == 1  # DMDB_ERR_ARG
+
+
+@pytest.mark.parametrize("engine", [1, 2])
+@pytest.mark.parametrize("which", ["A", "B"])
+def test_frozen_event_sequence(tab, system_a, system_b, hosttrace_lib, which, engine):
+    """the engine source (1-lane trace build) against the frozen oracle events of tests/golden/"""
+    from conftest import check_against_frozen_events, frozen_events
+    fx = frozen_events(which)
+    topo = (system_a if which == "A" else system_b)[0]
+    p = tables.make_params(boxl=float(fx["boxl"]), tstar=float(fx["tstar"]), canon=False, n_replicas=1, log_capacity=len(fx["t"]),
+                           engine=engine)
+    dev = DMD(p, topo, tab, lib_path=hosttrace_lib)
+    dev.set_state(fx["sv0"])
+    check_against_frozen_events(dev, fx, replica=0)

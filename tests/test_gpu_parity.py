@@ -241,6 +241,24 @@ def test_more_replicas_than_one_wave(tab, system_b):
         assert np.array_equal(big.calendar(r)[0], small.calendar(0)[0]), r
 
 
+@pytest.mark.parametrize("engine", [1, 2, 3])
+@pytest.mark.parametrize("which", ["A", "B"])
+def test_frozen_event_sequence(tab, system_a, system_b, which, engine):
+    """all three engines against the committed fixtures tests/golden/events_system{A,B}_nve.npz (the oracle's first
+    10^4 events, frozen): no oracle in the loop, the files are the reference"""
+    from conftest import check_against_frozen_events, frozen_events
+    fx = frozen_events(which)
+    topo = (system_a if which == "A" else system_b)[0]
+    R = 1 if engine == 3 else 2
+    p = tables.make_params(boxl=float(fx["boxl"]), tstar=float(fx["tstar"]), canon=False, n_replicas=R, log_capacity=len(fx["t"]),
+                           engine=engine)
+    dev = DMD(p, topo, tab)
+    dev.set_state(fx["sv0"])
+    if engine == 1:
+        dev.set_service_ctas(2)
+    check_against_frozen_events(dev, fx, replica=R - 1)
+
+
 def test_device_fill_matches_the_launch(tab):
     replicas, service = device_fill(0)
     assert replicas > 0 and replicas % 28 == 0 and service >= 0

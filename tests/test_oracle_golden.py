@@ -133,6 +133,22 @@ def test_thermostat_holds_temperature(tab, system_b):
     assert not o.checkover()[0]
 
 
+@pytest.mark.parametrize("which", ["A", "B"])
+def test_oracle_reproduces_its_frozen_event_sequence(tab, system_a, system_b, which):
+    """tests/golden/events_system{A,B}_nve.npz: the first 10^4 committed events (owner, partner, type, ev_code, time)
+    and the initial calendar, frozen from the oracle.  The reference has no golden vectors for these,
+    so this pins the oracle against its own history."""
+    from conftest import check_against_frozen_events, frozen_events
+    fx = frozen_events(which)
+    topo = (system_a if which == "A" else system_b)[0]
+    p = tables.make_params(boxl=float(fx["boxl"]), tstar=float(fx["tstar"]), canon=False, log_capacity=len(fx["t"]))
+    o = OracleDMD(p, topo, tab)
+    o.set_state(fx["sv0"])
+    check_against_frozen_events(o, fx)
+    e = o.energy()
+    assert abs(e.ered - float(fx["ered"])) < 1e-9 and [e.hb_alpha, e.hb_ii, e.hb_ij] == list(fx["hb"])
+
+
 def test_run_file_round_trip(tmp_path, system_a):
     topo, sv, boxl = system_a
     cfg, vel, bp = tmp_path / "run0001.config", tmp_path / "run0001.lastvel", tmp_path / "run0001.bptnr"
