@@ -36,6 +36,7 @@ def test_event_sequence_matches_oracle(tab, system_a, system_b, hosttrace_lib, w
     sa, sb = ora.stats(), dev.stats(0)
     assert list(sa.nevents) == list(sb.nevents)
     assert (sa.ghosts, sa.updates, sa.forced_updates) == (sb.ghosts, sb.updates, sb.forced_updates)
+    assert abs(sb.nbr_visits / sa.nbr_visits - 1.0) < 0.05  # work counters (roofline input): the oracle counts a cascaded bead per request
 
 
 @pytest.mark.parametrize("engine,warps", [(1, 0), (2, 3), (2, 16)])

@@ -36,6 +36,7 @@ def test_event_sequence_matches_oracle(tab, system_a, system_b, which, canon, n_
     sa, sb = ora.stats(), dev.stats(0)
     assert list(sa.nevents) == list(sb.nevents)
     assert (sa.ghosts, sa.updates, sa.forced_updates) == (sb.ghosts, sb.updates, sb.forced_updates)
+    assert abs(sb.nbr_visits / sa.nbr_visits - 1.0) < 0.05  # work counters (roofline input): the oracle counts a cascaded bead per request
     if canon:  # replica 3 draws from another RNG stream: compare it with its own oracle
         p3 = tables.make_params(boxl=boxl, tstar=0.5 if which == "A" else 0.18, canon=True, log_capacity=n_events, seed=p.seed + 3)
         o3 = OracleDMD(p3, topo, tab)
