@@ -6,6 +6,8 @@ Files, all under ``<workdir>/results``:
   runNNNN.config   ifort unformatted, appended records ``coll, t+tfalse, x[N], y[N], z[N]`` (config.f:16-24)
   runNNNN.bptnr    appended records ``coll, bptnr[N]`` (config.f:25-28)
   runNNNN.lastvel  one record ``coll, vx[N], vy[N], vz[N]``, rewritten at every output event (config.f:30-40)
+  runNNNN.pdb      final structure with built carbonyl oxygens (write_rasmol-YM.f, main.F90:1343-1346)
+  run(N-1).rca     side-chain bond audit of the restart structure, under the PREVIOUS run's number (inputinfo.f:413-505)
 Run numbering and restart chaining follow files_opn.f:19-46 and inputinfo.f:79-101: the new run takes the first
 unused number and restarts from the LAST record of the previous run's .config/.bptnr and its .lastvel.
 
@@ -123,6 +125,7 @@ def run_temperature(workdir: str, topo: Topology, tables: Tables, tstar: float, 
     written like the reference.  Returns a summary (run number, lines written, final energy record)."""
     files = RunFiles(workdir)
     sv, bp = files.restart(topo.n_beads)
+    fileio.write_rca(files.path(files.prev, "rca"), topo, tables, sv[:, :3], boxl)
     p = make_params(boxl=boxl, tstar=tstar, canon=canon, n_replicas=1, device=device, seed=seed, engine=engine)
     setemp = 12.0 * tstar
     lines = 0
@@ -166,6 +169,7 @@ def run_temperature(workdir: str, topo: Topology, tables: Tables, tstar: float, 
                                              e.hb_ii, e.hb_ij, e.ehh_ii, e.ehh_ij, rg, e2e))
         files.config(done, t_end, xyz, st["sv"][:, 3:], st["bptnr"])
         lines += 1
+        fileio.write_pdb(files.path(files.run, "pdb"), topo, xyz * boxl)  # after scale_up.f: Angstrom
         stats = d.stats(0)
     return dict(run=files.run, energy_lines=lines, events=done, ered=e.ered, tred=e.tred, hb=e.hb_ii + e.hb_ij,
                 ghosts=stats.ghosts, updates=stats.updates + stats.forced_updates)

@@ -43,6 +43,56 @@ def test_two_chained_runs_write_reference_style_files(tmp_path, tab, system_a, h
     assert np.array_equal(sv2[:, :3].T, xyz0)
     assert os.path.exists(res / "run0002.energy") and os.path.getsize(res / "run0002.config") > 0
     assert driver.first_unused_run(str(res)) == 3
+    # final PDB of each run (write_rasmol-YM.f) and the bond audit of the restart structure under the PREVIOUS number
+    _check_pdb(res / "run0001.pdb", topo, xyz0.T * boxl)
+    assert os.path.exists(res / "run0002.pdb")
+    rca = (res / "run0000.rca").read_text().splitlines()
+    n_side = sum(sum(sp.firstside) * sp.n_chains for sp in topo.species)
+    assert len([ln for ln in rca if ln[:3] in ("rca", "rnh", "rco")]) == 3 * n_side and os.path.exists(res / "run0001.rca")
+    assert not any("overlap" in ln for ln in rca)  # genconfig places every side chain inside its bond windows
+
+
+def _check_pdb(path, topo, xyz):
+    import re
+    lines = open(path).read().splitlines()
+    assert len(lines) == sum(sp.n_chains * (sp.numbeads + sp.chnln) for sp in topo.species)
+    pat = re.compile(r"^ATOM   [ \d*]{4}  (N |CA|C |O |CB)  [A-Z]{3} [AB][ \d]{4}    [ \-\d.]{24}$")
+    assert all(pat.match(ln) for ln in lines), [ln for ln in lines if not pat.match(ln)][:3]
+    pos = np.array([[float(ln[30:38]), float(ln[38:46]), float(ln[46:54])] for ln in lines])  # format 7: 3F8.3 from column 31
+    name = [ln[12:16].strip() for ln in lines]
+    sp = topo.species[0]
+    L = sp.chnln
+    # first chain: residue j has N = bead L+j, CA = bead j, C = bead 2L+j (1-based within the chain)
+    k = 0
+    nsc = 0
+    for j in range(L):
+        assert name[k:k + 4] == ["N", "CA", "C", "O"]
+        np.testing.assert_allclose(pos[k], xyz[L + j], atol=6e-4)
+        np.testing.assert_allclose(pos[k + 1], xyz[j], atol=6e-4)
+        np.testing.assert_allclose(pos[k + 2], xyz[2 * L + j], atol=6e-4)
+        assert abs(np.linalg.norm(pos[k + 3] - pos[k + 2]) - 1.231) < 3e-3  # the built carbonyl oxygen
+        if sp.firstside[j]:
+            assert name[k + 4] == "CB"
+            np.testing.assert_allclose(pos[k + 4], xyz[3 * L + nsc], atol=6e-4)
+            nsc += 1
+            k += 5
+        else:
+            k += 4
+
+
+def test_pdb_and_rca_of_the_shipped_snapshot(tmp_path, tab, system_a):
+    topo, sv, boxl = system_a
+    fileio.write_pdb(str(tmp_path / "a.pdb"), topo, sv[:, :3] * boxl)
+    _check_pdb(tmp_path / "a.pdb", topo, sv[:, :3] * boxl)
+    first = open(tmp_path / "a.pdb").readline().rstrip("\n")
+    assert first == "ATOM      1  N   GLY A   1      -0.597  -4.345  49.828"
+    lines = fileio.rca_lines(topo, tab, sv[:, :3], boxl)
+    assert lines[0] == "rca    1    2  2  2.0029  2.0020 "  # format 7373; the integer column is the reference's aa(k) = 2
+    # integers that do not fit their field print as asterisks, like the Fortran runtime does
+    big = tables.Topology([tables.Species.from_sequence("KLVFFAE", 300)])
+    xyz = np.zeros((big.n_beads, 3))
+    xyz[:, 0] = np.arange(big.n_beads) * 0.01
+    assert fileio.pdb_lines(big, xyz)[-1].startswith("ATOM   ****  CB  GLU A   7")
 
 
 def test_observables_on_the_shipped_snapshot(tab, system_a):
