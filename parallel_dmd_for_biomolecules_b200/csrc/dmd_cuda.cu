@@ -49,14 +49,14 @@ constexpr int BULK_THREADS = 256;  // CTA size of the thread-per-bead bulk kerne
 
 // read-only constants of the hot loop, copied into shared memory once per CTA
 struct SmemConsts {
-  PairTables tab;
+  HotTables tab;
   HotConst hot;
   double bl[6 * HOT_MAX_RES];
 };
 __device__ __forceinline__ Staged stage_consts(const DevArrays& d, SmemConsts* smem) {
   const double* src = reinterpret_cast<const double*>(d.tables);
   double* dst = reinterpret_cast<double*>(&smem->tab);
-  for (int k = threadIdx.x; k < (int)(sizeof(PairTables) / 8); k += blockDim.x) dst[k] = src[k];
+  for (int k = threadIdx.x; k < (int)(sizeof(HotTables) / 8); k += blockDim.x) dst[k] = src[k];  // the prefix of PairTables
   src = reinterpret_cast<const double*>(d.hot);
   dst = reinterpret_cast<double*>(&smem->hot);
   for (int k = threadIdx.x; k < (int)(sizeof(HotConst) / 8); k += blockDim.x) dst[k] = src[k];

@@ -26,7 +26,7 @@ namespace dmd {
 
 constexpr double T_PAD = 1e300;  // calendar padding entries
 #ifndef DMD_CQ_CAP
-#define DMD_CQ_CAP 160
+#define DMD_CQ_CAP 96
 #endif
 constexpr int CQ_CAP = DMD_CQ_CAP;  // per-warp scratch (shared memory on the device): the cascade queue ...
 constexpr int CQ_Q = CQ_CAP - 8;    // ... of CQ_Q entries (<= one per down-list candidate of the two main passes) and,
@@ -70,13 +70,13 @@ DMD_DEV void rep_load_scalars(Rep& r) {
 }
 
 struct Staged {  // the shared-memory copies of the read-only tables (global pointers in the host trace build)
-  const PairTables* tab;
+  const HotTables* tab;
   const HotConst* hot;
   const double* bl;
 };
 DMD_DEV Staged staged_global(const DevArrays& d) {
   Staged st;
-  st.tab = d.tables;
+  st.tab = reinterpret_cast<const HotTables*>(d.tables);  // HotTables is a prefix of PairTables
   st.hot = d.hot;
   st.bl = d.bl;
   return st;
@@ -1350,7 +1350,7 @@ DMD_DEV void energy_of(Rep& r, OutRec& o) {
       Geom g = pair_geom(rk, rj, r.tfalse);
       double rijsq = g.rx * g.rx + g.ry * g.ry + g.rz * g.rz;
       if (rijsq <= r.c.tab->welldia_sq[tix(rk.ident, rj.ident)]) {
-        double ep = r.c.tab->ep_sqrt[tix(rk.ident, rj.ident)];
+        double ep = r.c.sys->ep_sqrt[tix(rk.ident, rj.ident)];
         if (r.c.chain[k] == r.c.chain[j]) ehh_ii = ehh_ii + ep; else ehh_ij = ehh_ij + ep;
       }
     }

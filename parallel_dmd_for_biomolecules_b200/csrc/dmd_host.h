@@ -127,6 +127,8 @@ inline void build_model(const dmdb_params& p, const dmdb_topology& topo, const d
   SH(2, 4, hsq(s.shder[2])); SH(4, 2, hsq(s.shder[2])); SH(2, 8, hsq(s.shder[2])); SH(8, 2, hsq(s.shder[2]));
   s.eps1 = epsilon[1];
   s.eps_hb = pt.ep_sqrt[(5 - 1) * 28 + (8 - 1)];
+  std::memcpy(s.shlddia_sq, pt.shlddia_sq, sizeof(s.shlddia_sq));
+  std::memcpy(s.ep_sqrt, pt.ep_sqrt, sizeof(s.ep_sqrt));
   // ---- make_code.f:18-66 (ev_param)
   const double del = 0.02375;
   for (int l = 0; l <= 50; l++) s.ev_param1[l] = s.ev_param2[l] = s.ev_param3[l] = 1;

@@ -14,7 +14,7 @@ constexpr double T_NONE = 1000000000.0;  // events.f:28
 
 struct Ctx {                 // read-only context of one warp
   const SysConst* sys;       // global memory (cold fields only)
-  const PairTables* tab;     // shared-memory copy of the 28x28 tables
+  const HotTables* tab;      // shared-memory copy of sigma_sq / welldia_sq (the other two tables: sys, global memory)
   const HotConst* hot;       // shared-memory copy of the squeeze factors, bond windows of codes 4-9, masses
   const double* bl;          // per-residue side-chain bond windows (shared memory when nres <= HOT_MAX_RES)
   const uint32_t* meta;
@@ -135,7 +135,7 @@ DMD_DEV void pair_time_core(const Ctx& c, int code, double bij, double rijsq, do
         inside_force = -1;
       }
     } else {  // sqshlder.f
-      R2sq = c.tab->shlddia_sq[tix(idi, idj)];
+      R2sq = c.sys->shlddia_sq[tix(idi, idj)];
       t_leave = 10;
       t_enter = 12;
     }
@@ -225,7 +225,7 @@ DMD_DEV int event_dynamics(const Ctx& c, int ct, int code, BeadRec& a, BeadRec& 
     ratio = rmass * bij / sigsq;
   } else if (ct == 4 || ct == 8 || ct == 9) {
     double wellsq = c.tab->welldia_sq[tix(idi, idj)];
-    double epsave = c.tab->ep_sqrt[tix(idi, idj)];
+    double epsave = c.sys->ep_sqrt[tix(idi, idj)];
     double del_pe = 4.0 * wellsq * epsave / rmass;
     bumpdist = SMDIST * dmd_sqrt(wellsq);
     if (ct == 4) {
@@ -254,7 +254,7 @@ DMD_DEV int event_dynamics(const Ctx& c, int ct, int code, BeadRec& a, BeadRec& 
       sgn = 1.0;
     }
   } else if (ct == 5 || ct == 6 || ct == 13) {
-    double wellsq = c.tab->shlddia_sq[tix(idi, idj)];
+    double wellsq = c.sys->shlddia_sq[tix(idi, idj)];
     double epsave = -c.sys->eps1;
     double del_pe = 4.0 * wellsq * epsave / rmass;
     bumpdist = SMDIST * dmd_sqrt(wellsq);
@@ -347,7 +347,7 @@ DMD_DEV int event_dynamics_hot(const Ctx& c, int ct, int code, BeadRec& a, BeadR
 // bumped.f:12-43
 DMD_DEV void bump_off(const Ctx& c, int code, BeadRec& a, BeadRec& b, double tfalse) {
   const Geom g = pair_geom(a, b, tfalse);
-  double dsq = code >= 40 ? c.tab->shlddia_sq[tix(a.ident, b.ident)] : c.tab->welldia_sq[tix(a.ident, b.ident)];
+  double dsq = code >= 40 ? c.sys->shlddia_sq[tix(a.ident, b.ident)] : c.tab->welldia_sq[tix(a.ident, b.ident)];
   double bumpdist = SMDIST * dmd_sqrt(dsq);
   double sgn = g.bij < 0.0 ? -1.0 : 1.0;
   a.x = a.x + sgn * (bumpdist * g.rx);

@@ -54,12 +54,19 @@ constexpr uint32_t NB_MASK = (1u << NB_SHIFT) - 1;
 
 constexpr int MAX_RES = 512;   // residues over both species (bond-limit tables)
 
-// 28 x 28 pair tables of scale_down.f:37-67, index (id_i-1)*28 + (id_j-1); staged into shared memory
+// 28 x 28 pair tables of scale_down.f:37-67, index (id_i-1)*28 + (id_j-1)
 struct PairTables {
   double sigma_sq[784];
   double welldia_sq[784];
   double shlddia_sq[784];
   double ep_sqrt[784];
+};
+// the two tables every prediction reads (a prefix of PairTables): staged into shared memory.  Shoulder diameters and
+// well depths are needed by the rare H-bond / side-chain-well events only and stay in global memory (SysConst), so
+// that the event-loop CTA needs less than 32 KB of shared memory and the SM keeps 224 KB of L1
+struct HotTables {
+  double sigma_sq[784];
+  double welldia_sq[784];
 };
 
 // the constants every pair prediction / collision reads (a copy of the SysConst fields of the same name): staged
@@ -96,6 +103,8 @@ struct SysConst {
   double eps1;               // epsilon(1)
   double eps_hb;             // ep_sqrt(5,8), energy.f:74
   double hdelr, width, half, sig_max_all, boxl_orig;
+  double shlddia_sq[784];    // copies of PairTables.shlddia_sq / ep_sqrt (cold: shoulder events, well depths, energy)
+  double ep_sqrt[784];
   // per-residue side-chain bond limits, already multiplied out like bond.f:82-91:
   // [kind 0:R-Ca(10) 1:R-N(11) 2:R-C(12)][species residue index: species 0 -> r-1, species 1 -> chnln[0]+r-1]
   double blmin_sc[3][MAX_RES];
