@@ -684,16 +684,17 @@ inline bool block_engine_fits(const dmd::SysConst& s) {
   return dmd::blk_layout(s.N, s.ngroups * 32, smem_optin()).total <= smem_optin();
 }
 
-// Service split of the event-loop kernel (measured on B200, 48-peptide box, 158 us per rebuild, 148 CTAs in all:
-// 8 service CTAs 1.45e8, 12: 1.53e8, 16: 1.57e8, 18: 1.74e8, 20: 1.755e8, 22: 1.74e8, 24: 1.72e8 events/s; without
-// the service 1.38e8): about one service CTA per 6.4 event-loop CTAs
+// Service split of the event-loop kernel (measured on B200, 48-peptide box, 153 us per rebuild, 148 CTAs in all, final
+// round-1 build: 18 service CTAs 1.75e8 events/s -- the service saturates and warps take their requests back --, 20:
+// 2.02e8, 21: 2.07e8, 22: 2.04e8, 24: 2.05e8; without the service 1.5e8): about one service CTA per 5.7 event-loop
+// CTAs, on the safe side of the cliff
 inline int sm_count() {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   return sms;
 }
-inline int default_service_ctas(int worker_ctas) { return worker_ctas >= 32 ? (worker_ctas * 10 + 32) / 64 : 0; }
+inline int default_service_ctas(int worker_ctas) { return worker_ctas >= 32 ? (worker_ctas * 10 + 28) / 57 : 0; }
 inline void device_fill(int& replicas, int& service) {
   const int sms = sm_count();
   int w = sms;
