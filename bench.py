@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--replicas", type=int, default=0, help="replicas per GPU (0 = dmdb_device_fill: one 28-warp CTA per "
-                    "SM minus the list-rebuild service CTAs, 3528 on a 148-SM B200)")
+                    "SM minus the list-rebuild service CTAs, 3584 on a 148-SM B200)")
     ap.add_argument("--events", type=int, default=20000, help="calendar events per replica per step")
     ap.add_argument("--ref-events", type=int, default=400000, help="events per host thread per step (--impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -89,39 +89,50 @@ struct alignas(16) EvlSmem {
   SmemConsts consts;
   int32_t cq[WARPS_PER_CTA][CQ_CAP];
 };
+#ifndef DMD_SVC_GROUPS
+#define DMD_SVC_GROUPS 2  // a service CTA works as this many independent groups of warps, one replica each: with one
+                          // bead per thread a 1344-bead replica leaves a third of 896 threads idle in its second round
+#endif
+__device__ __forceinline__ void svc_group_sync(int grp, int gsz) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(gsz) : "memory"); }
+
 __device__ __noinline__ void svc_serve_in_kernel(DevArrays d, int r0, int nrep, unsigned char* scratch, size_t scratch_bytes) {
-  __shared__ int s_pick, s_state;
+  __shared__ int s_pick[DMD_SVC_GROUPS], s_state[DMD_SVC_GROUPS];
   const Staged tab = staged_global(d);
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int gsz = ((int)blockDim.x / 32 / DMD_SVC_GROUPS) * 32;  // threads per group (whole warps)
+  const int grp = (int)threadIdx.x / gsz;
+  if (grp >= DMD_SVC_GROUPS) return;  // left-over warps
+  const int tid = (int)threadIdx.x - grp * gsz, nt = gsz;
+  scratch_bytes /= DMD_SVC_GROUPS;
+  scratch += (size_t)grp * scratch_bytes;
   const bool grid_fits = ((size_t)d.ncc3 + 2 * (size_t)d.n_beads) * 4 <= scratch_bytes;
   int32_t* const s_heads = reinterpret_cast<int32_t*>(scratch);
   int32_t* const s_cnext = s_heads + d.ncc3;
   uint32_t* const s_cpk = reinterpret_cast<uint32_t*>(s_cnext + d.n_beads);
-  const int scan0 = (int)(((long long)blockIdx.x * nrep) / (int)gridDim.x);
+  const int scan0 = (int)(((long long)(blockIdx.x * DMD_SVC_GROUPS + grp) * nrep) / ((int)gridDim.x * DMD_SVC_GROUPS));
   while (true) {
-    if (tid == 0) s_pick = 0x7fffffff;
-    __syncthreads();
+    if (tid == 0) s_pick[grp] = 0x7fffffff;
+    svc_group_sync(grp, gsz);
     for (int k = tid; k < nrep; k += nt) {
       int idx = k + scan0;
       if (idx >= nrep) idx -= nrep;
       if (*(volatile int32_t*)(d.svc_flag + r0 + idx) == 1) {
-        atomicMin(&s_pick, idx);
+        atomicMin(&s_pick[grp], idx);
         break;
       }
     }
-    __syncthreads();
-    const int pick = s_pick;
+    svc_group_sync(grp, gsz);
+    const int pick = s_pick[grp];
     if (tid == 0) {
       if (pick == 0x7fffffff) {
         const unsigned long long done = *(volatile unsigned long long*)&d.svc_ctl[0];
-        s_state = done >= (unsigned long long)nrep ? 2 : 0;
-        if (s_state == 0) __nanosleep(1000);
+        s_state[grp] = done >= (unsigned long long)nrep ? 2 : 0;
+        if (s_state[grp] == 0) __nanosleep(1000);
       } else {
-        s_state = svc_cas_acq_rel(d.svc_flag + r0 + pick, 1, 2) == 1 ? 1 : 0;
+        s_state[grp] = svc_cas_acq_rel(d.svc_flag + r0 + pick, 1, 2) == 1 ? 1 : 0;
       }
     }
-    __syncthreads();
-    const int state = s_state;
+    svc_group_sync(grp, gsz);
+    const int state = s_state[grp];
     if (state == 2) return;
     if (state == 0) continue;
     const long long t0 = clock64();
@@ -134,19 +145,19 @@ __device__ __noinline__ void svc_serve_in_kernel(DevArrays d, int r0, int nrep, 
       q.cellhead = s_heads;
       q.cnext = s_cnext;
       q.cpk = s_cpk;
-      __syncthreads();
+      svc_group_sync(grp, gsz);
     }
     cell_build(q, tid, nt);
-    __syncthreads();
+    svc_group_sync(grp, gsz);
     nbor_build(q, tid, nt);
     if (!grid_fits) {
-      __syncthreads();
+      svc_group_sync(grp, gsz);
       cell_clear(q, tid, nt);
     }
     for (int l = tid; l < q.N; l += nt) redo_lane(q, l);  // events.f:23-107; the requester refreshes the group minima
     if (q.error && Warp::lane() == 0 && atomicCAS(&q.sc->error, 0, q.error) == 0) q.sc->error_info = q.error_info;
     __threadfence();
-    __syncthreads();
+    svc_group_sync(grp, gsz);
     if (tid == 0) {
       svc_st_release(d.svc_flag + rid, 0);
       atomicAdd(&d.svc_ctl[4], (unsigned long long)(clock64() - t0));
@@ -684,17 +695,17 @@ inline bool block_engine_fits(const dmd::SysConst& s) {
   return dmd::blk_layout(s.N, s.ngroups * 32, smem_optin()).total <= smem_optin();
 }
 
-// Service split of the event-loop kernel (measured on B200, 48-peptide box, 153 us per rebuild, 148 CTAs in all, final
-// round-1 build: 18 service CTAs 1.75e8 events/s -- the service saturates and warps take their requests back --, 20:
-// 2.02e8, 21: 2.07e8, 22: 2.04e8, 24: 2.05e8; without the service 1.5e8): about one service CTA per 5.7 event-loop
-// CTAs, on the safe side of the cliff
+// Service split of the event-loop kernel (measured on B200, 48-peptide box, 148 CTAs in all, final round-1 build with
+// two service groups per CTA, 131 us per rebuild and CTA: 14 service CTAs 1.73e8 events/s, 16: 1.80e8 -- the service
+// saturates and warps take their requests back --, 18: 2.11e8, 20: see DESIGN.md, 22: 2.08e8; without the service
+// 1.5e8): about one service CTA per 6.4 event-loop CTAs, on the safe side of the cliff
 inline int sm_count() {
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   return sms;
 }
-inline int default_service_ctas(int worker_ctas) { return worker_ctas >= 32 ? (worker_ctas * 10 + 28) / 57 : 0; }
+inline int default_service_ctas(int worker_ctas) { return worker_ctas >= 32 ? (worker_ctas * 10 + 32) / 64 : 0; }
 inline void device_fill(int& replicas, int& service) {
   const int sms = sm_count();
   int w = sms;

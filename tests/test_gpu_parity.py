@@ -269,8 +269,8 @@ def test_device_fill_matches_the_launch(tab):
 
 
 def test_full_size_properties(tab, system_b):
-    """BASELINE config 2 at bench size: the replica count that fills the device (dmdb_device_fill: 3528 replicas of the
-    48-peptide box on a 148-SM B200, next to 22 list-rebuild service CTAs).  Size-independent properties:
+    """BASELINE config 2 at bench size: the replica count that fills the device (dmdb_device_fill: 3584 replicas of the
+    48-peptide box on a 148-SM B200, next to 20 list-rebuild service CTAs).  Size-independent properties:
     NVE energy is conserved in every replica, every replica's final state passes checkover.f (sampled), identical
     replicas stay bit-identical, and a second run of the same handle state is deterministic."""
     topo, sv, boxl = system_b
