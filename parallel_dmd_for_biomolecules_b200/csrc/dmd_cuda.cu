@@ -1,7 +1,9 @@
 // dmd_cuda.cu -- libdmdb200.so: CUDA backend (sm_100a) of the C ABI in include/dmdb200.h.
 //
-// Kernels (one warp per replica; 28 replicas per CTA; the 28x28 pair tables and hot constants are staged in shared memory):
-//   dmd_event_loop_kernel    the persistent event loop, main.F90:484-1258 (dmdb_run, engine 1: warp per replica)
+// Kernels (one warp per replica; 28 replicas per CTA; the two 28x28 tables every prediction reads and the hot constants
+// are staged in shared memory):
+//   dmd_event_loop_kernel    the persistent event loop, main.F90:484-1258 (dmdb_run, engine 1: warp per replica); its
+//                            first CTAs are the list-rebuild service (nbor.f + events.f for the other CTAs' replicas)
 //   dmd_block_loop_kernel    the same loop with one CTA per replica, state in shared memory, batched
 //                            conservative commit of independent events (dmdb_run, engine 2; dmd_block.h)
 //   dmd_grid_loop_kernel     the same rounds spread over every SM for ONE large system (dmdb_run, engine 3; dmd_grid.h)
@@ -38,8 +40,8 @@ namespace dmd {
 
 #ifndef DMD_WPC
 #define DMD_WPC 28  // one 28-warp CTA per SM (72 registers per thread) shares ONE shared-memory copy of the tables.
-                    // Measured on B200 (48-peptide box): 16 warps 1.13e8, 20: 1.18e8, 24: 1.21e8, 28: 1.32e8 events/s --
-                    // the loop is bound by dependent latencies, so resident warps beat the extra spills
+                    // Measured on B200 (48-peptide box), final round-1 build with the service split: 24 warps
+                    // 1.67e8, 28: 1.93e8, 32 (64 registers): 1.90e8 events/s
 #endif
 constexpr int WARPS_PER_CTA = DMD_WPC;
 constexpr int BULK_THREADS = 256;  // CTA size of the thread-per-bead bulk kernels
