@@ -25,10 +25,39 @@
 #include <stdexcept>
 #include <string>
 
-#include "dmd_block.h"
-#include "dmd_engine.h"
-#include "dmd_grid.h"
 #include "dmd_types.h"
+
+// The engine source is compiled once per lane count (dmd_warp.h), each time into its own namespace:
+//   dmd::w32 (inline: plain dmd:: names)  32 lanes per replica -- CTA-per-replica and whole-GPU engines, bulk kernels
+//   dmd::evl                              DMD_EVL_W lanes per replica -- the warp-per-replica event loop (engine 1)
+#ifndef DMD_EVL_W
+#define DMD_EVL_W 16  // two replicas per hardware warp (measured on B200, 48-peptide box: see DESIGN.md section 4)
+#endif
+#define DMD_W 32
+#define DMD_VARIANT_BEGIN inline namespace w32 {
+#define DMD_VARIANT_END }
+#include "dmd_block.h"
+#include "dmd_grid.h"
+#undef DMD_W
+#undef DMD_VARIANT_BEGIN
+#undef DMD_VARIANT_END
+#if DMD_EVL_W != 32
+#define DMD_W DMD_EVL_W
+#define DMD_VARIANT_BEGIN namespace evl {
+#define DMD_VARIANT_END }
+#include "dmd_engine.h"
+#if DMD_EVL_W == 16
+#include "dmd_lockstep.h"  // the hot path of two replicas per hardware warp, executed in lockstep
+#endif
+#undef DMD_W
+#undef DMD_VARIANT_BEGIN
+#undef DMD_VARIANT_END
+#else
+namespace dmd {
+namespace evl = w32;
+}
+#endif
+#define DMD_W 32
 
 #define CUDA_OK(x)                                                                                   \
   do {                                                                                               \
@@ -44,6 +73,8 @@ namespace dmd {
                     // 1.67e8, 28: 1.93e8, 32 (64 registers): 1.90e8 events/s
 #endif
 constexpr int WARPS_PER_CTA = DMD_WPC;
+constexpr int EVL_RPW = 32 / DMD_EVL_W;            // replicas per hardware warp of the event loop
+constexpr int EVL_RPC = WARPS_PER_CTA * EVL_RPW;   // ... and per CTA
 constexpr int BULK_THREADS = 256;  // CTA size of the thread-per-bead bulk kernels
 #ifndef DMD_MIN_CTAS
 #define DMD_MIN_CTAS 1
@@ -55,7 +86,8 @@ struct SmemConsts {
   HotConst hot;
   double bl[6 * HOT_MAX_RES];
 };
-__device__ __forceinline__ Staged stage_consts(const DevArrays& d, SmemConsts* smem) {
+template <class ST>
+__device__ __forceinline__ ST stage_consts_t(const DevArrays& d, SmemConsts* smem) {
   const double* src = reinterpret_cast<const double*>(d.tables);
   double* dst = reinterpret_cast<double*>(&smem->tab);
   for (int k = threadIdx.x; k < (int)(sizeof(HotTables) / 8); k += blockDim.x) dst[k] = src[k];  // the prefix of PairTables
@@ -66,12 +98,13 @@ __device__ __forceinline__ Staged stage_consts(const DevArrays& d, SmemConsts* s
   if (bl_fits)
     for (int k = threadIdx.x; k < 6 * d.nres; k += blockDim.x) smem->bl[k] = d.bl[k];
   __syncthreads();
-  Staged st;
+  ST st;
   st.tab = &smem->tab;
   st.hot = &smem->hot;
   st.bl = bl_fits ? smem->bl : d.bl;
   return st;
 }
+__device__ __forceinline__ Staged stage_consts(const DevArrays& d, SmemConsts* smem) { return stage_consts_t<Staged>(d, smem); }
 
 __device__ __forceinline__ int32_t* warp_queue() {
   __shared__ int32_t s_cq[WARPS_PER_CTA][CQ_CAP];
@@ -89,7 +122,7 @@ __device__ __forceinline__ int replica_of_warp(int r0, int nrep) {
 // cascade queues, which a service CTA does not use); bead records and tables are read through L1/L2.
 struct alignas(16) EvlSmem {
   SmemConsts consts;
-  int32_t cq[WARPS_PER_CTA][CQ_CAP];
+  int32_t cq[EVL_RPC][evl::CQ_CAP];
 };
 #ifndef DMD_SVC_GROUPS
 #define DMD_SVC_GROUPS 2  // a service CTA works as this many independent groups of warps, one replica each: with one
@@ -99,7 +132,7 @@ __device__ __forceinline__ void svc_group_sync(int grp, int gsz) { asm volatile(
 
 __device__ __noinline__ void svc_serve_in_kernel(DevArrays d, int r0, int nrep, unsigned char* scratch, size_t scratch_bytes) {
   __shared__ int s_pick[DMD_SVC_GROUPS], s_state[DMD_SVC_GROUPS];
-  const Staged tab = staged_global(d);
+  const evl::Staged tab = evl::staged_global(d);
   const int gsz = ((int)blockDim.x / 32 / DMD_SVC_GROUPS) * 32;  // threads per group (whole warps)
   const int grp = (int)threadIdx.x / gsz;
   if (grp >= DMD_SVC_GROUPS) return;  // left-over warps
@@ -130,7 +163,7 @@ __device__ __noinline__ void svc_serve_in_kernel(DevArrays d, int r0, int nrep, 
         s_state[grp] = done >= (unsigned long long)nrep ? 2 : 0;
         if (s_state[grp] == 0) __nanosleep(1000);
       } else {
-        s_state[grp] = svc_cas_acq_rel(d.svc_flag + r0 + pick, 1, 2) == 1 ? 1 : 0;
+        s_state[grp] = evl::svc_cas_acq_rel(d.svc_flag + r0 + pick, 1, 2) == 1 ? 1 : 0;
       }
     }
     svc_group_sync(grp, gsz);
@@ -139,8 +172,8 @@ __device__ __noinline__ void svc_serve_in_kernel(DevArrays d, int r0, int nrep, 
     if (state == 0) continue;
     const long long t0 = clock64();
     const int rid = r0 + pick;
-    Rep q;
-    rep_bind(q, d, tab, nullptr, rid);  // scalars as saved by the requesting warp (tfalse = 0, new interval_max)
+    evl::Rep q;
+    evl::rep_bind(q, d, tab, nullptr, rid);  // scalars as saved by the requesting warp (tfalse = 0, new interval_max)
     q.error = 0;
     if (grid_fits) {
       for (int k = tid; k < d.ncc3; k += nt) s_heads[k] = -1;
@@ -149,19 +182,19 @@ __device__ __noinline__ void svc_serve_in_kernel(DevArrays d, int r0, int nrep, 
       q.cpk = s_cpk;
       svc_group_sync(grp, gsz);
     }
-    cell_build(q, tid, nt);
+    evl::cell_build(q, tid, nt);
     svc_group_sync(grp, gsz);
-    nbor_build(q, tid, nt);
+    evl::nbor_build(q, tid, nt);
     if (!grid_fits) {
       svc_group_sync(grp, gsz);
-      cell_clear(q, tid, nt);
+      evl::cell_clear(q, tid, nt);
     }
-    for (int l = tid; l < q.N; l += nt) redo_lane(q, l);  // events.f:23-107; the requester refreshes the group minima
-    if (q.error && Warp::lane() == 0 && atomicCAS(&q.sc->error, 0, q.error) == 0) q.sc->error_info = q.error_info;
+    for (int l = tid; l < q.N; l += nt) evl::redo_lane(q, l);  // events.f:23-107; the requester refreshes the group minima
+    if (q.error && evl::Warp::lane() == 0 && atomicCAS(&q.sc->error, 0, q.error) == 0) q.sc->error_info = q.error_info;
     __threadfence();
     svc_group_sync(grp, gsz);
     if (tid == 0) {
-      svc_st_release(d.svc_flag + rid, 0);
+      evl::svc_st_release(d.svc_flag + rid, 0);
       atomicAdd(&d.svc_ctl[4], (unsigned long long)(clock64() - t0));
       atomicAdd(&d.svc_ctl[1], 1ull);
     }
@@ -175,19 +208,42 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, DMD_MIN_CTAS) dmd_event_lo
     svc_serve_in_kernel(d, r0, nrep, reinterpret_cast<unsigned char*>(&sm), sizeof(EvlSmem));
     return;
   }
-  const Staged tab = stage_consts(d, &sm.consts);
-  const int w = ((int)blockIdx.x - n_srv) * WARPS_PER_CTA + (threadIdx.x >> 5);
+  const evl::Staged tab = stage_consts_t<evl::Staged>(d, &sm.consts);
+  const int wl = (int)threadIdx.x / DMD_EVL_W;  // this replica's slot in the CTA (DMD_EVL_W lanes each)
+  const int w = ((int)blockIdx.x - n_srv) * EVL_RPC + wl;
+#if DMD_EVL_W == 16
+  const bool pair = __all_sync(0xffffffffu, w < nrep);  // both halves of this hardware warp hold a replica
+#endif
   if (w >= nrep) return;
   const int rid = r0 + w;
-  Rep r;
-  rep_bind(r, d, tab, sm.cq[threadIdx.x >> 5], rid);
+  evl::Rep r;
+  evl::rep_bind(r, d, tab, sm.cq[wl], rid);
   if (n_srv > 0) {
     r.svc = d.svc_flag + rid;
     r.svc_ctl = d.svc_ctl;
   }
-  if (r.error == 0) run_events(r, n_events, (flags & 1) != 0);
-  rep_save(r);
-  if (n_srv > 0 && Warp::lane() == 0) atomicAdd(&d.svc_ctl[0], 1ull);  // the service CTAs leave when all warps are done
+#if defined(DMD_PHASE_PROF)
+  __shared__ unsigned long long s_prof[EVL_RPC][16];
+  r.prof = s_prof[wl];
+  if (evl::Warp::lane() == 0) {
+    for (int k = 0; k < 15; k++) r.prof[k] = 0;
+    r.prof[15] = (unsigned long long)clock64();
+  }
+  evl::Warp::sync();
+#endif
+#if DMD_EVL_W == 16
+  if (pair) evl::lk_run_events(r, n_events, (flags & 1) != 0);  // two replicas per warp in lockstep
+  else if (r.error == 0) evl::run_events(r, n_events, (flags & 1) != 0);
+#else
+  if (r.error == 0) evl::run_events(r, n_events, (flags & 1) != 0);
+#endif
+#if defined(DMD_PHASE_PROF)
+  evl::Warp::sync();
+  if (evl::Warp::lane() == 0)
+    for (int k = 0; k < 15; k++) atomicAdd(&evl::g_phase_cyc[k], r.prof[k]);
+#endif
+  evl::rep_save(r);
+  if (n_srv > 0 && evl::Warp::lane() == 0) atomicAdd(&d.svc_ctl[0], 1ull);  // the service CTAs leave when all warps are done
 }
 
 // ---- CTA-per-replica engine -----------------------------------------------------------------------------------
@@ -707,12 +763,12 @@ inline int sm_count() {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   return sms;
 }
-inline int default_service_ctas(int worker_ctas) { return worker_ctas >= 32 ? (worker_ctas * 10 + 32) / 64 : 0; }
+inline int default_service_ctas(int worker_ctas) { return worker_ctas >= 32 ? (worker_ctas * 10 + 26) / 52 : 0; }
 inline void device_fill(int& replicas, int& service) {
   const int sms = sm_count();
   int w = sms;
   while (w > 1 && w + default_service_ctas(w) > sms) w--;
-  replicas = w * dmd::WARPS_PER_CTA;
+  replicas = w * dmd::EVL_RPC;
   service = default_service_ctas(w);
 }
 
@@ -857,7 +913,8 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
                    double* ms, int* launches, int flags = 0) {
   using namespace dmd;
   const int block = WARPS_PER_CTA * 32;
-  const int grid = (nrep + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  const int grid = (nrep + WARPS_PER_CTA - 1) / WARPS_PER_CTA;  // 32-lane kernels: one replica per hardware warp
+  const int grid_evl = (nrep + EVL_RPC - 1) / EVL_RPC;          // event loop: DMD_EVL_W lanes per replica
   int nl = 1;
   CUDA_OK(cudaEventRecord(g_ev0, g_stream));
   switch (op) {
@@ -880,22 +937,41 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
         if (sv || asked >= 0) {
           const int want = sv ? atoi(sv) : asked;
           n_srv = want < sms - 1 ? want : sms - 1;
-        } else if (grid <= sms) {  // one wave: as many service CTAs as fit beside the event-loop CTAs
-          const int want = default_service_ctas(grid);
-          n_srv = want < sms - grid ? want : sms - grid;
+        } else if (grid_evl <= sms) {  // one wave: as many service CTAs as fit beside the event-loop CTAs
+          const int want = default_service_ctas(grid_evl);
+          n_srv = want < sms - grid_evl ? want : sms - grid_evl;
           if (3 * n_srv < want) n_srv = 0;  // too few would only make the warps wait (measured: 4 of 22 is a loss)
         } else {  // several waves: event-loop CTAs take turns on the SMs the service CTAs leave free, if that is faster
           int w = sms, srv = 0;
           device_fill(w, srv);
-          w /= WARPS_PER_CTA;
+          w /= EVL_RPC;
           // per event-loop SM: 1.37e6 events/s with the service, 0.93e6 without
-          if (srv > 0 && ((grid + w - 1) / w) / 1.37 < ((grid + sms - 1) / sms) / 0.93) n_srv = srv;
+          if (srv > 0 && ((grid_evl + w - 1) / w) / 1.37 < ((grid_evl + sms - 1) / sms) / 0.93) n_srv = srv;
         }
         if (n_srv < 0) n_srv = 0;
       }
       flags &= 0xff;
       if (n_srv > 0) CUDA_OK(cudaMemsetAsync(d.svc_ctl, 0, SVC_CTL_WORDS * 8, g_stream));
-      dmd_event_loop_kernel<<<grid + n_srv, block, 0, g_stream>>>(d, r0, nrep, arg, flags, n_srv);
+#if defined(DMD_PHASE_PROF)
+      {
+        unsigned long long z[16] = {0};
+        CUDA_OK(cudaMemcpyToSymbolAsync(evl::g_phase_cyc, z, sizeof(z), 0, cudaMemcpyHostToDevice, g_stream));
+      }
+#endif
+      dmd_event_loop_kernel<<<grid_evl + n_srv, block, 0, g_stream>>>(d, r0, nrep, arg, flags, n_srv);
+#if defined(DMD_PHASE_PROF)
+      if (getenv("DMDB_DEBUG")) {
+        unsigned long long c[16];
+        CUDA_OK(cudaStreamSynchronize(g_stream));
+        CUDA_OK(cudaMemcpyFromSymbol(c, evl::g_phase_cyc, sizeof(c)));
+        const double ev = (double)nrep * (double)arg;
+        static const char* nm[8] = {"flush", "pop", "pair_event", "main pass", "cascade prep", "cascade pass", "cold", "loop"};
+        double tot = 0;
+        for (int k = 0; k < 8; k++) tot += (double)c[k];
+        for (int k = 0; k < 8; k++) fprintf(stderr, "phase %-13s %9.1f cycles/event  %5.1f %%\n", nm[k], c[k] / ev, 100.0 * c[k] / tot);
+        fprintf(stderr, "phase total         %9.1f cycles/event\n", tot / ev);
+      }
+#endif
       if (n_srv > 0 && getenv("DMDB_DEBUG")) {
         unsigned long long ctl[SVC_CTL_WORDS];
         d2h(ctl, d.svc_ctl, sizeof(ctl));

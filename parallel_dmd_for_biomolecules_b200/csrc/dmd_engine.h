@@ -9,8 +9,8 @@
 //   cell_build/nbor_build/predict_all (cell_add.f, nbor.f, events.f) with one lane per bead (cold)
 // The hot loop is kept small (it must live in the instruction cache while 16+ warps per SM sit at different
 // program counters); everything rare is __noinline__ and takes the replica view by value.
-// Every loop is written for DMD_W lanes (32 on the device, 1 in the host trace build).
-#pragma once
+// Every loop is written for DMD_W lanes per replica (dmd_warp.h: 32 or 16 on the device, 1 in the host trace build).
+// No include guard: dmd_cuda.cu includes this file once per lane count, each time in its own namespace.
 #include "dmd_physics.h"
 #include "dmd_topology.h"
 #include "dmd_types.h"
@@ -23,7 +23,10 @@
 #endif
 
 namespace dmd {
+DMD_VARIANT_BEGIN
 
+constexpr int WLOG = DMD_W == 32 ? 5 : (DMD_W == 16 ? 4 : (DMD_W == 8 ? 3 : 0));  // log2(DMD_W)
+static_assert((1 << WLOG) == DMD_W, "DMD_W must be 1, 8, 16 or 32");
 constexpr double T_PAD = 1e300;  // calendar padding entries
 #ifndef DMD_CQ_CAP
 #define DMD_CQ_CAP 96
@@ -34,8 +37,27 @@ constexpr int CQ_Q = CQ_CAP - 8;    // ... of CQ_Q entries (<= one per down-list
                                     // pass, they would otherwise sit in (and be spilled from) registers -- the
                                     // counters alone measured +7 % events/s
 
+// optional phase profile of the warp-per-replica loop (-DDMD_PHASE_PROF, tools only): lane 0 of every warp adds the
+// SM clocks since its previous mark to a per-warp shared-memory slot; the kernel sums the slots into g_phase_cyc
+#if defined(DMD_PHASE_PROF) && !defined(DMD_HOST_TRACE)
+__device__ unsigned long long g_phase_cyc[16];
+#define DMD_PROF_MARK(r, k)                                                    \
+  do {                                                                         \
+    if ((r).prof && Warp::lane() == 0) {                                       \
+      const unsigned long long now_ = (unsigned long long)clock64();          \
+      (r).prof[k] += now_ - (r).prof[15];                                      \
+      (r).prof[15] = now_;                                                     \
+    }                                                                          \
+  } while (0)
+#else
+#define DMD_PROF_MARK(r, k) do { } while (0)
+#endif
+
 struct Rep {
   Ctx c;
+#if defined(DMD_PHASE_PROF) && !defined(DMD_HOST_TRACE)
+  unsigned long long* prof = nullptr;
+#endif
   int N, cap, G;
   BeadRec* rec;
   CalEnt* cal;
@@ -210,8 +232,14 @@ DMD_DEV void flush_dirty(Rep& r) {
   while (dirty0) {  // two groups per round so that their loads overlap
     const int g0 = pop_lowest_bit(dirty0);
     const int g1 = dirty0 ? pop_lowest_bit(dirty0) : -1;
-    double x0 = r.cal[g0 * 32 + Warp::lane()].t;
-    double x1 = g1 >= 0 ? r.cal[g1 * 32 + Warp::lane()].t : 0.0;
+    double x0 = T_PAD, x1 = T_PAD;
+#pragma unroll
+    for (int q = Warp::lane(); q < 32; q += DMD_W) {
+      const double y0 = r.cal[g0 * 32 + q].t;
+      const double y1 = g1 >= 0 ? r.cal[g1 * 32 + q].t : T_PAD;
+      x0 = y0 < x0 ? y0 : x0;
+      x1 = y1 < x1 ? y1 : x1;
+    }
     x0 = warp_min(x0);
     if (g1 >= 0) x1 = warp_min(x1);
     if (Warp::lane() == 0) {
@@ -281,7 +309,7 @@ DMD_DEV int pop_min(Rep& r, CalEnt& ev) {
   int wkey = key;
   warp_argmin(wv, wkey);
 #if DMD_W > 1
-  const int src = wkey & 31;  // the owning lane (one entry per lane when DMD_W == 32)
+  const int src = wkey & (DMD_W - 1);  // the lane that scanned the winning entry holds it as its own best
   pt = Warp::shfl(pt, src);
   ty = Warp::shfl(ty, src);
 #endif
@@ -332,21 +360,6 @@ struct ListRef {
   int nu, nd;
 };
 
-// (value, key) arg-min over the lanes of `mask` (a segment of the warp); all lanes of the segment get the result
-DMD_DEV void seg_argmin(double& v, int& key, unsigned mask) {
-#if DMD_W > 1
-  unsigned hi, lo;
-  ord_split(v, hi, lo);
-  const unsigned mhi = __reduce_min_sync(mask, hi);
-  const bool c1 = hi == mhi;
-  const unsigned mlo = __reduce_min_sync(mask, c1 ? lo : 0xffffffffu);
-  const bool c2 = c1 && lo == mlo;
-  const unsigned mkey = __reduce_min_sync(mask, c2 ? (unsigned)key : 0xffffffffu);
-  v = ord_join(mhi, mlo);
-  key = (int)mkey;
-#endif
-}
-
 // the two halves of a bead record: integer part (partners, identity, overlay codes) / positions and velocities
 DMD_DEV void rec_load_tail(BeadRec& dst, const BeadRec* src) {
 #if DMD_W > 1
@@ -371,181 +384,266 @@ DMD_DEV void rec_load_head(BeadRec& dst, const BeadRec* src) {
 }
 
 // ONE pass = ONE copy of the prediction code in the hot loop (the loop must stay resident in the instruction
-// cache while every warp of the SM sits at a different program counter).  The warp is split into G = 1, 2 or 4
-// segments of SEG lanes; segment g handles bead beads[g]:
-//   main pass      G = 1, with_down: all items of a colliding bead (full items feed the running minimum of the
-//                  bead, down items lower cal[b] -- eventredo_down.f:70-77 -- or queue b for a cascade)
-//   cascade pass   G beads at once, full items only (events.f:26-57 for one bead each)
+// cache while every warp of the SM sits at a different program counter).  A lane works for ONE bead `a` during the
+// whole pass and takes the items q = q0, q0 + stride, ... < T of that bead:
+//   [0, nu)            up-list partners b > a: "full" items, they feed the running minimum of a (events.f:26-57)
+//   [nu, nu+nd)        down-list beads l < a (main pass only): they lower cal[l] -- eventredo_down.f:70-77 -- or
+//                      queue l for a cascade when nptnr(l) == a (partial_events.f:73-96)
+//   [nu+nd, nu+nd+3)   aux slots extra_repuls(a,1:3), present only when one of them is set: b > a is a full item
+//                      (events.f:77), b < a a down item (partial_events.f:100,166)
+// Lane mappings:
+//   main pass, two beads  the items of BOTH colliding beads in one trip when they fit the lanes (lanes [0, T_i) bead
+//                         i, [T_i, T_i + T_j) bead j).  The down items of i are applied first, then -- after a warp
+//                         sync, re-reading the entries -- those of j: the order of the Fortran (down(i), then
+//                         down(j)).  Returns false without touching j when the items do not fit, or when j holds i
+//                         in an aux slot (its down item on cal[i] must see the entry full(i) writes at the end of
+//                         the pass): the caller then gives j a pass of its own.
+//   main pass, one bead   all lanes (ghost event; bead j after a `false` above; every main pass of the 1-lane build)
+//   cascade pass          1, 2 or 4 queued beads at once, full items only (events.f:26-57 for one bead each)
 template <bool BLK>
-DMD_DEV void segmented_pass(Rep& r, int a, bool act, int sh, bool with_down, int skip, const ListRef* lr, int& cqn,
-                            Undo* u) {
+DMD_DEV bool prediction_pass(Rep& r, const bool main_pass, const int i, const int j, const int skip1, const ListRef* li,
+                             const ListRef* lj, const int idx, const int rem, int& cqn, Undo* u) {
+  const int lane = Warp::lane();
+  const int cap = r.cap;
+  int a, q0, ssh, nu, nd, er3, skip, T;
+  bool act = true, second = false, two = false;
+  unsigned segmask = WARP_ALL;  // the lanes (bit k = lane k) that work for the same bead as this lane
+  uint32_t e0 = 0, ma;
+  BeadRec ra;  // of the lane's own bead only the integer part (partners, identity, overlay) is held across the pass;
+               // positions and velocities are fetched again (L1) where the geometry is formed
+  const ListRef* lra = nullptr;  // where later trips find the lists of the lane's bead (nullptr: the replica's arrays)
+  if (main_pass) {
+    two = DMD_W > 1 && j >= 0;
+    const int jj = two ? j : i;
+    const uint32_t* const upi = li ? li->up : r.up + (size_t)i * cap;
+    const uint32_t* const dni = li ? li->dn : r.dn + (size_t)i * cap;
+    const uint32_t* const upj = two ? (lj ? lj->up : r.up + (size_t)jj * cap) : upi;
+    const uint32_t* const dnj = two ? (lj ? lj->dn : r.dn + (size_t)jj * cap) : dni;
+    // ---- level-1 loads, all independent: before the list lengths are known every lane fetches "its" entry of the
+    // four lists; the lane that ends up with item q of a list takes it from lane q by a shuffle
 #if DMD_W > 1
-  const int SEG = DMD_W >> sh;
-  const int g = Warp::lane() >> (5 - sh), pl = Warp::lane() & (SEG - 1);
-  const unsigned segmask = (sh == 0 ? 0xffffffffu : ((1u << SEG) - 1u)) << (g * SEG);
+    uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    if (lane < cap) {
+      s0 = upi[lane];
+      s1 = dni[lane];
+      if (two) {
+        s2 = upj[lane];
+        s3 = dnj[lane];
+      }
+    }
+#endif
+    BeadRec ti, tj;
+    (rec_load_tail)(ti, &r.rec[i]);
+    (rec_load_tail)(tj, &r.rec[jj]);
+    const int nu_i = li ? li->nu : (int)r.nup[i], nd_i = li ? li->nd : (int)r.ndn[i];
+    const int nu_j = lj ? lj->nu : (int)r.nup[jj], nd_j = lj ? lj->nd : (int)r.ndn[jj];
+    const int e3i = r.er34[2 * i], e3j = r.er34[2 * jj];
+    const uint32_t mi = r.c.meta[i], mj = r.c.meta[jj];
+    int Ti = nu_i + nd_i + ((ti.er1 >= 0 || ti.er2 >= 0 || e3i >= 0) ? 3 : 0);
+    int Tj = nu_j + nd_j + ((tj.er1 >= 0 || tj.er2 >= 0 || e3j >= 0) ? 3 : 0);
+    Ti = Ti > 0 ? Ti : 1;  // a bead without items still needs a lane that writes its calendar entry
+    Tj = Tj > 0 ? Tj : 1;
+    if (two && (Ti + Tj > DMD_W || tj.er1 == i || tj.er2 == i || e3j == i)) two = false;  // j gets its own pass
+    {  // work counters (roofline input): slots and list entries of the bead(s) of this pass
+      unsigned* c = warp_counters(r);
+      const unsigned slots = (unsigned)(nu_i + nd_i + 6 + (two ? nu_j + nd_j + 6 : 0));
+      const unsigned visits = (unsigned)(nu_i + nd_i + (two ? nu_j + nd_j : 0));
+      if (lane == 0) {
+#if DMD_W > 1
+        atomicAdd(&c[0], slots);
+        atomicAdd(&c[1], visits);
 #else
-  const int SEG = 1, pl = 0;
-  const unsigned segmask = 1u;
+        c[0] += slots;
+        c[1] += visits;
 #endif
-  // ---- level-1 loads, all independent: record, list lengths and (before the lengths are known) the first SEG
-  // entries of the lists, one per lane
-  const size_t lbase = (size_t)a * r.cap;
-  const uint32_t* const upl = lr ? lr->up : r.up + lbase;
-  const uint32_t* const dnl = lr ? lr->dn : r.dn + lbase;
+      }
+    }
+    q0 = lane;
+    ssh = WLOG;
+    if (two) {
+      second = lane >= Ti;
+      q0 = second ? lane - Ti : lane;
+      const unsigned m1 = (1u << Ti) - 1u;  // Ti < DMD_W here
+      segmask = second ? WARP_ALL & ~m1 : m1;
+    }
+    a = second ? j : i;
+    nu = second ? nu_j : nu_i;
+    nd = second ? nd_j : nd_i;
+    T = second ? Tj : Ti;
+    er3 = second ? e3j : e3i;
+    ma = second ? mj : mi;
+    skip = second ? i : skip1;
+    ra.bptnr = second ? tj.bptnr : ti.bptnr;
+    ra.er1 = second ? tj.er1 : ti.er1;
+    ra.er2 = second ? tj.er2 : ti.er2;
+    ra.ident = second ? tj.ident : ti.ident;
+    ra.ov1 = second ? tj.ov1 : ti.ov1;
+    ra.ov2 = second ? tj.ov2 : ti.ov2;
+    ra.pad = 0;
+    lra = second ? lj : li;
 #if DMD_W > 1
-  uint32_t eu0 = 0, ed0 = 0;
-  if (pl < r.cap) {
-    eu0 = upl[pl];
-    if (with_down) ed0 = dnl[pl];
-  }
+    {  // the entry of the lane's first item
+      const bool isup = q0 < nu;
+      const int src = (isup ? q0 : q0 - nu) & (DMD_W - 1);
+      const uint32_t t0 = (uint32_t)Warp::shfl((int)s0, src), t1 = (uint32_t)Warp::shfl((int)s1, src);
+      const uint32_t t2 = (uint32_t)Warp::shfl((int)s2, src), t3 = (uint32_t)Warp::shfl((int)s3, src);
+      e0 = second ? (isup ? t2 : t3) : (isup ? t0 : t1);
+    }
 #endif
-  // of the bead's own record only the integer part (partners, identity, overlay) is held across the pass; positions
-  // and velocities are fetched again (L1) where the geometry is formed, so that they do not occupy twelve registers
-  // while the partners' records are in flight and the predictor runs
-  BeadRec ra;
-  rec_load_tail(ra, &r.rec[a]);
-  const uint32_t ma = r.c.meta[a];
-  const int nu = act ? (lr ? lr->nu : (int)r.nup[a]) : -3;
-  const int nd = with_down ? (lr ? lr->nd : (int)r.ndn[a]) : 0;
-  const int er3 = r.er34[2 * a];
-  const int nF = nu + 3, total = with_down ? nF + nd + 3 : nF;
-  int tmax = total;
+  } else {
+    // cascades, several beads per pass: segment count by the queue length only (no size look-up: that would put a
+    // dependent load in front of the pass); a list longer than its segment takes another trip
 #if DMD_W > 1
-  if (sh) tmax = (int)__reduce_max_sync(0xffffffffu, (unsigned)(total > 0 ? total : 0));
-#endif
-  if (pl == 0 && act) {  // the first lane of every segment
-    unsigned* c = warp_counters(r);
-#if DMD_W > 1
-    atomicAdd(&c[0], (unsigned)total);
-    atomicAdd(&c[1], (unsigned)(with_down ? nu + nd : nu));
+    const int sh = rem >= 3 ? 2 : (rem == 2 ? 1 : 0);
+    const int SEG = DMD_W >> sh;
+    const int g = lane >> (WLOG - sh);
+    segmask = (sh == 0 ? WARP_ALL : ((1u << SEG) - 1u)) << (g * SEG);
+    q0 = lane & (SEG - 1);
+    ssh = WLOG - sh;
 #else
-    c[0] += (unsigned)total;
-    c[1] += (unsigned)(with_down ? nu + nd : nu);
+    const int g = 0;
+    q0 = 0;
+    ssh = 0;
 #endif
+    act = g < rem;
+    a = r.cq[idx + (act ? g : 0)];
+#if DMD_W > 1
+    if (q0 < cap) e0 = r.up[(size_t)a * cap + q0];
+#endif
+    (rec_load_tail)(ra, &r.rec[a]);
+    ma = r.c.meta[a];
+    nu = (int)r.nup[a];
+    nd = 0;
+    er3 = r.er34[2 * a];
+    T = act ? nu + ((ra.er1 >= 0 || ra.er2 >= 0 || er3 >= 0) ? 3 : 0) : 0;
+    if (act && T == 0) T = 1;
+    skip = -1;
+    if (q0 == 0 && act) {
+      unsigned* c = warp_counters(r);
+#if DMD_W > 1
+      atomicAdd(&c[0], (unsigned)(nu + 3));
+      atomicAdd(&c[1], (unsigned)nu);
+#else
+      c[0] += (unsigned)(nu + 3);
+      c[1] += (unsigned)nu;
+#endif
+    }
   }
+  int ntrip = T > q0 ? (T - q0 + (1 << ssh) - 1) >> ssh : 0;
+  ntrip = warp_max_u(ntrip);
   double best = r.interval_max + LTSTEP - r.tfalse;
   int bpos = 0x7fffffff, bj = -1, btype = -1;
 #pragma unroll 1
-  for (int base = 0; base < tmax; base += SEG) {
-    const int p = base + pl;
+  for (int trip = 0, q = q0; trip < ntrip; trip++, q += 1 << ssh) {
     int b = -1, sc = 1;  // the other bead of the pair and the pair's static class
-    const bool full = p < nF;
-    const int q = p - nF;  // index into the down list
-#if DMD_W > 1
-    const uint32_t edq = (uint32_t)Warp::shfl((int)ed0, q & 31);  // main pass only (G = 1)
-#endif
-    if (p < nu) {
-#if DMD_W > 1
-      const uint32_t e = base == 0 ? eu0 : upl[p];
-#else
-      const uint32_t e = upl[p];
-#endif
+    bool full = false;
+    if (q < nu + nd) {
+      const bool isup = q < nu;
+      full = isup;
+      uint32_t e = e0;
+      if (DMD_W == 1 || trip > 0) {  // later trips (long lists): a dependent load
+        const uint32_t* const lst = lra ? (isup ? lra->up : lra->dn) : (isup ? r.up : r.dn) + (size_t)a * cap;
+        e = lst[isup ? q : q - nu];
+      }
       b = (int)(e & NB_MASK);
       sc = (int)(e >> NB_SHIFT);
-    } else if (p < nF) {
-      const int k = p - nu;
+      if (!isup && b == skip) b = -1;  // partial_events.f:136
+    } else if (q < T) {
+      const int k = q - nu - nd;
       b = k == 0 ? ra.er1 : (k == 1 ? ra.er2 : er3);
-      if (b <= a) b = -1;  // events.f:77
-    } else if (q < nd) {
-#if DMD_W > 1
-      const uint32_t e = q < 32 ? edq : dnl[q];
-#else
-      const uint32_t e = dnl[q];
-#endif
-      b = (int)(e & NB_MASK);
-      sc = (int)(e >> NB_SHIFT);
-      if (b == skip) b = -1;  // partial_events.f:136
-    } else if (p < total) {
-      const int k = q - nd;
-      b = k == 0 ? ra.er1 : (k == 1 ? ra.er2 : er3);
-      if (!(b >= 0 && b < a)) b = -1;  // partial_events.f:100,166
+      full = b > a;                                 // events.f:77
+      if (b < 0 || (!full && !main_pass)) b = -1;  // partial_events.f:100,166
     }
-    bool need_full = false;
-    int changed = -1;
-    double lowered_t = 0.0;
+    if (q >= T) b = -1;  // an idle cascade segment (T == 0) has no items
+    const bool down = b >= 0 && !full;
+    const bool late = two && second;  // j's down items are decided after i's, on re-read entries
+    double tij = T_NONE;
+    int type = -1;
     CalEnt eb;
     eb.t = 0.0; eb.ptnr = -1; eb.type = -1;
     if (b >= 0) {
       // level-2 loads, all depending on b only (+ the position / velocity part of a's own record)
       const BeadRec rb = r.rec[b];
-      rec_load_head(ra, &r.rec[a]);
+      (rec_load_head)(ra, &r.rec[a]);
       uint32_t mlo = ma;
       if (!full) {
-        eb = r.cal[b];
         mlo = r.c.meta[b];
+        if (!late) eb = r.cal[b];
       }
-      if (!full && eb.ptnr == a) {
-        need_full = true;  // l's next event was with a: full re-prediction of l (cascade)
+      const int code = overlay_code(sc, a, ra, b, rb);
+      {  // one prediction site for both orientations (owner = lower index: a when full, b otherwise)
+        const Geom gm = pair_geom(ra, rb, r.tfalse);
+        const double rijsq = gm.rx * gm.rx + gm.ry * gm.ry + gm.rz * gm.rz;
+        const double vijsq = gm.vx * gm.vx + gm.vy * gm.vy + gm.vz * gm.vz;
+        const int idlo = full ? ra.ident : rb.ident, idhi = full ? rb.ident : ra.ident;
+        const bool bonded = full ? ra.bptnr == b : rb.bptnr == a;
+        pair_time_core(r.c, code, gm.bij, rijsq, vijsq, idlo, idhi, mlo, bonded, tij, type);
+      }
+      if (full) {
+        if (tij < best) {  // strict: first in evaluation order wins (events.f:53)
+          best = tij;
+          bpos = q;
+          bj = b;
+          btype = pack_type(type, sc);
+        }
       } else {
-        const int code = overlay_code(sc, a, ra, b, rb);
-        double tij = T_NONE;
-        int type = -1;
-        {  // one prediction site for both orientations (owner = lower index: a when full, b otherwise)
-          const Geom gm = pair_geom(ra, rb, r.tfalse);
-          const double rijsq = gm.rx * gm.rx + gm.ry * gm.ry + gm.rz * gm.rz;
-          const double vijsq = gm.vx * gm.vx + gm.vy * gm.vy + gm.vz * gm.vz;
-          const int idlo = full ? ra.ident : rb.ident, idhi = full ? rb.ident : ra.ident;
-          const bool bonded = full ? ra.bptnr == b : rb.bptnr == a;
-          pair_time_core(r.c, code, gm.bij, rijsq, vijsq, idlo, idhi, mlo, bonded, tij, type);
-        }
-        if (full) {
-          if (tij < best) {  // strict: first in evaluation order wins (events.f:53)
-            best = tij;
-            bpos = p;
-            bj = b;
-            btype = pack_type(type, sc);
-          }
-        } else {  // eventredo_down.f:70-77
-          tij = tij + r.tfalse;
-          if (tij < eb.t) {
-            CalEnt ne;
-            ne.t = tij;
-            ne.ptnr = a;
-            ne.type = pack_type(type, sc);
-            r.cal[b] = ne;
-            changed = b;
-            lowered_t = tij;
-            if (BLK && tij < u->newmin) u->newmin = tij;
-          }
-        }
+        tij = tij + r.tfalse;
       }
     }
-    if (with_down) {
-      if (BLK) {  // undo log of the lowered entries (eb = the old entry of this lane's bead)
-        const unsigned mc = Warp::ballot(changed >= 0);
-        if (mc) {
-          const int pos = u->n + dmd_popc(mc & ((1u << Warp::lane()) - 1u));
-          if (changed >= 0 && pos < u->cap) {
-            u->idx[pos] = changed;
-            u->old[pos] = eb;
-          }
-          u->n += dmd_popc(mc);
+    if (main_pass) {
+#pragma unroll 1
+      for (int ph = 0; ph < (two ? 2 : 1); ph++) {
+        const bool mine = down && late == (ph == 1);
+        if (ph == 1) {
+          Warp::sync();  // j's operations re-read the entries i's operations may have lowered
+          if (mine) eb = r.cal[b];
         }
-      } else if (changed >= 0) {
-        // an entry that was only LOWERED: the group minimum follows with an integer atomicMin on its ordered image
-        // (exact -- no rescan of the group's 32 entries); entries that may rise (the writer below) mark the group
+        const bool need_full = mine && eb.ptnr == a;  // l's next event was with a: full re-prediction of l (cascade)
+        const bool lower = mine && !need_full && tij < eb.t;  // eventredo_down.f:70-77
+        if (lower) {
+          CalEnt ne;
+          ne.t = tij;
+          ne.ptnr = a;
+          ne.type = pack_type(type, sc);
+          r.cal[b] = ne;
+          if (BLK && tij < u->newmin) u->newmin = tij;
+        }
+        if (BLK) {  // undo log of the lowered entries (eb = the old entry of this lane's bead)
+          const unsigned mc = Warp::ballot(lower);
+          if (mc) {
+            const int pos = u->n + dmd_popc(mc & ((1u << lane) - 1u));
+            if (lower && pos < u->cap) {
+              u->idx[pos] = b;
+              u->old[pos] = eb;
+            }
+            u->n += dmd_popc(mc);
+          }
+        } else if (lower) {
+          // an entry that was only LOWERED: the group minimum follows with an integer atomicMin on its ordered image
+          // (exact -- no rescan of the group's 32 entries); entries that may rise (the writer below) mark the group
 #if DMD_W > 1
-        atomicMin(&r.tmin1[changed >> 5], ord_bits64(lowered_t));
+          atomicMin(&r.tmin1[b >> 5], ord_bits64(tij));
 #else
-        if (ord_bits64(lowered_t) < r.tmin1[changed >> 5]) r.tmin1[changed >> 5] = ord_bits64(lowered_t);
+          if (ord_bits64(tij) < r.tmin1[b >> 5]) r.tmin1[b >> 5] = ord_bits64(tij);
 #endif
-      }
-      const unsigned m = Warp::ballot(need_full);
-      if (m) {
-        const int pos = cqn + dmd_popc(m & ((1u << Warp::lane()) - 1u));
-        if (need_full && pos < CQ_Q) r.cq[pos] = b;
-        cqn += dmd_popc(m);
+        }
+        const unsigned m = Warp::ballot(need_full);
+        if (m) {
+          const int pos = cqn + dmd_popc(m & ((1u << lane) - 1u));
+          if (need_full && pos < CQ_Q) r.cq[pos] = b;
+          cqn += dmd_popc(m);
+        }
       }
     }
   }
-  // ---- the minimum of each segment's full items -> cal[a]; the lane that holds it writes the entry (a segment
-  // without any event: its first lane)
+  // ---- the minimum of each bead's full items -> cal[a]; the lane that holds it writes the entry (a bead without
+  // any event: its first lane)
   double wbest = best;
   int wpos = bpos;
   seg_argmin(wbest, wpos, segmask);
   const bool mine = act && bpos == wpos && bpos != 0x7fffffff;
   const unsigned any_mine = Warp::ballot(mine) & segmask;
-  const bool writer = act && (any_mine ? mine : pl == 0);
+  const bool writer = act && (any_mine ? mine : q0 == 0);
   CalEnt ne;
   ne.t = wbest + r.tfalse;
   ne.ptnr = any_mine ? bj : -1;
@@ -558,7 +656,7 @@ DMD_DEV void segmented_pass(Rep& r, int a, bool act, int sh, bool with_down, int
   }
   if (BLK) {
     const unsigned mw = Warp::ballot(writer);
-    const int pos = u->n + dmd_popc(mw & ((1u << Warp::lane()) - 1u));
+    const int pos = u->n + dmd_popc(mw & ((1u << lane) - 1u));
     if (writer && pos < u->cap) {
       u->idx[pos] = a;
       u->old[pos] = old;
@@ -568,6 +666,7 @@ DMD_DEV void segmented_pass(Rep& r, int a, bool act, int sh, bool with_down, int
   } else {
     mark_dirty_lanes(r, writer ? a : -1);
   }
+  return two;
 }
 
 DMD_DEV void repuls_del_b(Rep& r, int n, int cb);
@@ -575,19 +674,19 @@ DMD_DEV void repuls_del_b(Rep& r, int n, int cb);
 template <bool BLK>
 DMD_DEV void partial_events_t(Rep& r, int i, int j, bool xpulse_del, Undo* u, const ListRef* li, const ListRef* lj) {
   Warp::sync();
-  int cqn = 0, stage = 0, idx = 0;
+  int cqn = 0, idx = 0;
+  int stage = 0;  // 0 main pass (both beads, or bead i), 1 bead j alone, 2 prepare the cascade queue, 3 cascades
 #pragma unroll 1
   while (true) {
-    int a, skip = -1, sh = 0;
-    bool with_down, act = true;
-    const ListRef* lr = nullptr;
-    if (stage < 2) {  // the two colliding beads, one after the other
-      a = stage == 0 ? i : j;
-      skip = stage == 0 ? -1 : i;
-      lr = stage == 0 ? li : lj;
-      stage++;
-      if (a < 0) continue;  // ghost event: one bead only (main.F90:1049)
-      with_down = true;
+    int pi = i, pj = -1, skip = -1, rem = 0;
+    const ListRef *l1 = li, *l2 = nullptr;
+    if (stage == 0) {
+      pj = j;  // j < 0: ghost event, one bead only (main.F90:1049)
+      l2 = lj;
+    } else if (stage == 1) {
+      pi = j;
+      skip = i;
+      l1 = lj;
     } else {
       if (stage == 2) {  // all down items are done: prepare the cascade queue
         stage = 3;
@@ -616,23 +715,16 @@ DMD_DEV void partial_events_t(Rep& r, int i, int j, bool xpulse_del, Undo* u, co
           cqn = keep_n;
         }
       }
+      DMD_PROF_MARK(r, 4);
       if (idx >= cqn) break;
-      // cascades, several beads per pass: segment count by the queue length only (no size look-up: that would
-      // put a dependent load in front of the pass); a list longer than its segment takes another trip
-      const int rem = cqn - idx;
-#if DMD_W > 1
-      sh = rem >= 3 ? 2 : (rem == 2 ? 1 : 0);
-      const int g = Warp::lane() >> (5 - sh);
-#else
-      const int g = 0;
-#endif
-      act = g < rem;
-      a = r.cq[idx + (act ? g : 0)];
-      idx += rem < (1 << sh) ? rem : (1 << sh);
-      with_down = false;
+      rem = cqn - idx;
     }
-    segmented_pass<BLK>(r, a, act, sh, with_down, skip, lr, cqn, u);
-    Warp::sync();  // j's operations re-read the entries i's operations may have lowered
+    const bool both = prediction_pass<BLK>(r, stage < 2, pi, pj, skip, l1, l2, idx, rem, cqn, u);
+    Warp::sync();  // later passes re-read the entries this one may have lowered
+    DMD_PROF_MARK(r, stage < 2 ? 3 : 5);
+    if (stage == 0) stage = (j >= 0 && !both) ? 1 : 2;
+    else if (stage == 1) stage = 2;
+    else idx += DMD_W > 1 ? (rem >= 3 ? (rem < 4 ? rem : 4) : rem) : 1;
   }
   if (xpulse_del) {
     if (Warp::lane() == 0) {
@@ -1023,7 +1115,7 @@ DMD_DEV void cell_build(Rep& r, int t0 = Warp::lane(), int ts = DMD_W) {
   Warp::sync();
   for (int k = t0; k < r.N; k += ts) {
     int cx, cy, cz;
-    cell_coords(s, r.rec[k], cx, cy, cz);
+    (cell_coords)(s, r.rec[k], cx, cy, cz);
     r.cellof[k] = 1 + (cx + nw) + (cy + nw) * nc + (cz + nw) * nc * nc;  // cell_add.f:25
     if (cx < 0 || cy < 0 || cz < 0 || cx >= ncr || cy >= ncr || cz >= ncr) {
       // the reference would file the bead in a ghost cell that is never looked up
@@ -1153,7 +1245,11 @@ DMD_DEV void nbor(Rep& r) {  // nbor.f:33-137
 // clears the word.  release/acquire at gpu scope on the word orders the replica's arrays between the two SMs (the
 // acquire also drops the stale L1 lines).  A request nobody claims within SVC_PATIENCE cycles is taken back
 // (1 -> 3) and served in place, so the loop never depends on a service CTA being resident.
-constexpr long long SVC_PATIENCE = 4000000;      // ~2 ms
+#ifndef DMD_SVC_PATIENCE
+#define DMD_SVC_PATIENCE 80000000  // ~40 ms: a rebuild done in place drags the rebuild code through the event-loop SM's
+                                   // instruction cache and stalls the warp's other replica (measured: 2 ms -> 40 ms +15 %)
+#endif
+constexpr long long SVC_PATIENCE = DMD_SVC_PATIENCE;
 constexpr long long SVC_TIMEOUT = 4000000000ll;  // ~2 s in state 2: report an error instead of hanging
 DMD_DEV int svc_ld_relaxed(const int32_t* p) {  // polling: no L1 invalidation (the other warps of the SM keep their lines)
   int v;
@@ -1406,6 +1502,7 @@ DMD_DEV void process_one(Rep& r, int o, const CalEnt& ev) {
   bool xpulse_del = false, redo = true;
   if (o < r.N) {
     xpulse_del = pair_event(r, o, ev);
+    DMD_PROF_MARK(r, 2);
   } else {
     rep_save(r);  // hand the scalars to the out-of-line handler through r.sc ...
     if (o == r.N) {
@@ -1421,15 +1518,19 @@ DMD_DEV void process_one(Rep& r, int o, const CalEnt& ev) {
     clear_dirty(r);
     Warp::sync();
     if (redo) mark_dirty(r, r.N >> 5);  // the next ghost time
+    DMD_PROF_MARK(r, 6);
   }
   if (redo) partial_events(r, pi, pj, xpulse_del);  // main.F90:943, :1049 -- the only call site in the loop
 }
 
 // returns the owner index of the processed calendar entry, or -1 on error
 DMD_DEV int step(Rep& r) {
+  DMD_PROF_MARK(r, 7);
   flush_dirty(r);
+  DMD_PROF_MARK(r, 0);
   CalEnt ev;
   const int o = pop_min(r, ev);
+  DMD_PROF_MARK(r, 1);
   if (o < 0) {
     set_error(r, DMD_E_CAL_EMPTY, 0);
     return -1;
@@ -1705,4 +1806,5 @@ DMD_DEV void init_replica(Rep& r, const double* sv, const int32_t* bptnr1, doubl
   Warp::sync();
 }
 
+DMD_VARIANT_END
 }  // namespace dmd

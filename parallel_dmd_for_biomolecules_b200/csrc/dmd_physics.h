@@ -3,8 +3,8 @@
 // /root/reference/parallel-dmd-PRIME20/code).  Arithmetic contract (DESIGN.md "fp64 discipline"): IEEE fp64,
 // operations in the order the Fortran writes them, NO FMA contraction (nvcc -fmad=false), dnint == round().
 #pragma once
+#include "dmd_math.h"
 #include "dmd_types.h"
-#include "dmd_warp.h"
 
 namespace dmd {
 

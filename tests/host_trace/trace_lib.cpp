@@ -5,6 +5,7 @@
 // diffed against the oracle in the GPU-less build container (tests/test_engine_logic_hosttrace.py).
 // It exercises none of the 32-lane collectives; the real parity tests are the `-m gpu` ones.
 #define DMD_HOST_TRACE 1
+#define DMD_W 1  // one lane per replica (dmd_warp.h)
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
@@ -15,8 +16,7 @@
 #include <thread>
 #include <vector>
 
-#include "../../parallel_dmd_for_biomolecules_b200/csrc/dmd_block.h"
-#include "../../parallel_dmd_for_biomolecules_b200/csrc/dmd_engine.h"
+#include "../../parallel_dmd_for_biomolecules_b200/csrc/dmd_block.h"  // includes dmd_engine.h (no include guard: once)
 #include "../../parallel_dmd_for_biomolecules_b200/csrc/dmd_types.h"
 
 // The CTA-per-replica engine (dmd_block.h) is emulated with one host thread per (1-lane) virtual warp; its
