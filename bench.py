@@ -4,9 +4,12 @@
 Metric (BASELINE.json): DMD collision events/s per B200 (every processed calendar event, counted like the
 reference's `coll`, main.F90:639).  Workload at N=1: BASELINE config 2 -- the 48-peptide Abeta16-22 (KLVFFAE)
 PRIME20 box, N = 1344 beads, L = 158.54 A, T* = 0.18, Andersen thermostat on (-Dcanon) -- as an ensemble of R
-independent replicas resident on one GPU (one warp per replica; the replica count is the one that fills the device in
-one wave next to the list-rebuild service CTAs of the same kernel, dmdb_device_fill).  N>1: the same per-GPU workload on every GPU
-(weak scaling) plus one replica-exchange collective (NCCL all-gather of (E_pot, T*)) per step.
+independent replicas resident on one GPU (two replicas per hardware warp, 16 lanes each, in lockstep; the replica
+count is the one that fills the device in one wave next to the list-rebuild service CTAs of the same kernel,
+dmdb_device_fill).  N>1: BASELINE config 3 -- the same box count per GPU (weak scaling), but the replicas form
+11-temperature ladders (temp_018 ... temp_050, qfile/script.sh:11-18) whose members are striped across the GPUs, with
+one replica-exchange step per bench step: dmdb_exchange = energy reduction + ncclAllGather of (E_pot, T*) over NVLink
++ Metropolis decision + temperature change of the swapped replicas, all on the device and inside the timed region.
 
 A "step" = every replica advances `--events` calendar events (one launch of the persistent event-loop kernel).
 
@@ -36,6 +39,8 @@ sys.path.insert(0, ROOT)
 METRIC = "DMD collision events/sec per B200"
 UNIT = "events/s"
 WORKLOAD = "config2: 48 x Abeta16-22 (KLVFFAE) PRIME20 box, N=1344 beads, L=158.54 A, T*=0.18, canon"
+WORKLOAD_LADDER = ("config3: 48 x Abeta16-22 (KLVFFAE) PRIME20 boxes, N=1344 beads, L=158.54 A, canon, as 11-temperature "
+                   "ladders T*=0.18..0.50 (temp_018..temp_050) striped across the GPUs, replica exchange every step")
 TSTAR, BOXL = 0.18, 158.54
 
 
@@ -45,10 +50,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--replicas", type=int, default=0, help="replicas per GPU (0 = dmdb_device_fill: one 28-warp CTA per "
-                    "SM minus the list-rebuild service CTAs, 3584 on a 148-SM B200)")
+    ap.add_argument("--replicas", type=int, default=0, help="replicas per GPU (0 = dmdb_device_fill: one 28-warp CTA (56 replicas) per "
+                    "SM minus the list-rebuild service CTAs, 7168 on a 148-SM B200)")
     ap.add_argument("--events", type=int, default=20000, help="calendar events per replica per step")
     ap.add_argument("--ref-events", type=int, default=400000, help="events per host thread per step (--impl reference)")
+    ap.add_argument("--ladder", action="store_true", help="config 3 on one GPU too: 11-temperature ladders + exchange per step "
+                    "(always on for --gpus > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (single trajectory, "
                     "12 288-bead box, bulk kernels on a 10^6-bead box)")
@@ -266,12 +273,25 @@ def main():
     p = tables.make_params(boxl=BOXL, tstar=TSTAR, canon=True, n_replicas=R, device=local_rank, seed=1058472402 + 100003 * rank)
     d = DMD(p, topo, tab)
     d.set_state(sv)
+    ladder = world > 1 or args.ladder
+    xch = {"ms": 0.0, "attempted": 0, "accepted": 0, "changed": 0, "ladders": 0, "launches": 0}
+    if ladder:  # BASELINE config 3: the reference's 11 temperatures, ladders striped across the GPUs
+        replica_exchange.init_communicator(d)  # the library's own NCCL communicator (dmdb_comm_init)
+        d.apply_temperatures(replica_exchange.ladder_temperatures(world, rank, R))
 
-    def step(k):
-        st = d.run(E)
-        if world > 1:  # the replica-set exchange; equal temperatures -> decisions are no-ops
-            replica_exchange.exchange_step(d, k, seed=4242, device=dev)
-        return st.device_ms
+    def step(k, timed=False):
+        ms = d.run(E).device_ms
+        if ladder:  # dmdb_exchange: energies -> ncclAllGather -> decision -> retemp, on the library's stream
+            st = d.exchange(k, seed=4242, ladder_size=len(replica_exchange.LADDER))
+            ms += st.device_ms
+            if timed:
+                xch["ms"] += st.device_ms
+                xch["attempted"] += st.attempted
+                xch["accepted"] += st.accepted
+                xch["changed"] += st.changed_local
+                xch["ladders"] = st.ladders
+                xch["launches"] += st.kernel_launches
+        return ms
 
     for k in range(args.warmup):
         step(k)
@@ -282,7 +302,7 @@ def main():
     t0 = time.perf_counter()
     dev_ms = 0.0
     for k in range(args.steps):
-        dev_ms += step(args.warmup + k)
+        dev_ms += step(args.warmup + k, timed=True)
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -335,11 +355,19 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "replicas_per_gpu": R, "beads_per_replica": N, "events_per_replica_per_step": E,
-                       "parallelism": "one warp per replica, %d replicas per GPU, %d GPU(s)%s; per GPU %d event-loop CTAs + "
-                                      "%s list-rebuild service CTAs in ONE kernel" % (
-                           R, world, ", NCCL all-gather replica exchange per step" if world > 1 else "",
-                           (R + 27) // 28, service_ctas if R == fill_replicas else "auto"),
+            "config": {"workload": WORKLOAD if not ladder else WORKLOAD_LADDER, "replicas_per_gpu": R, "beads_per_replica": N,
+                       "events_per_replica_per_step": E,
+                       "parallelism": "two replicas per hardware warp (16 lanes each, lockstep), %d replicas per GPU, %d GPU(s)%s; "
+                                      "per GPU %d event-loop CTAs + %s list-rebuild service CTAs in ONE kernel" % (
+                           R, world, ", dmdb_exchange (ncclAllGather + device-side decision + retemp) per step" if ladder else "",
+                           (R + 55) // 56, service_ctas if R == fill_replicas else "auto"),
+                       "exchange": None if not ladder else {
+                           "ladders": xch["ladders"], "ladder_size": len(replica_exchange.LADDER),
+                           "pairs_attempted_per_step": xch["attempted"] / args.steps,
+                           "swap_acceptance": xch["accepted"] / max(xch["attempted"], 1),
+                           "local_replicas_retempered_per_step": xch["changed"] / args.steps,
+                           "device_ms_per_step": xch["ms"] / args.steps,
+                           "what": "energy kernel + pack + ncclAllGather + decide + select + retemp kernels on the library's stream, inside ms_per_step"},
                        "l2": "no flush needed: resident working set per GPU %.1f GB >> 126 MB L2" % (R * N * 1100 / 1e9),
                        "event_count_convention": "all calendar events incl. ghost/interval pseudo-events (main.F90:639)",
                        "pair_event_fraction": d_pair / max(d_events, 1),
@@ -351,7 +379,7 @@ def main():
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "path": "dmdb_set_state_all(pinned host sv,bptnr) -> dmdb_run -> dmdb_sync_positions -> "
                             "dmdb_get_state_all + dmdb_potential_energies"},
-            "gpu_launches": args.steps * (1 + (2 if world > 1 else 0)),  # event loop (+ energy and retemp kernels of the exchange)
+            "gpu_launches": args.steps + xch["launches"],  # event-loop kernel per step (+ the exchange's own kernels)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "dmd_event_loop_kernel",
                          "algorithmic_bytes_per_launch": abytes / args.steps,

@@ -79,7 +79,7 @@ typedef struct dmdb_params {
   int32_t n_replicas;   /* independent trajectories held by this handle (one warp each on the device) */
   int32_t device;       /* CUDA device ordinal */
   int32_t nbr_capacity; /* per-bead capacity of the up and of the down neighbour list (0 = default 64) */
-  int32_t log_capacity; /* per-replica event-log ring capacity in events (0 = no log) */
+  int32_t log_capacity; /* per-replica event-log capacity in events (0 = no log); logging stops when it is full */
   int32_t engine;       /* event-loop engine: 0 = automatic, 1 = one warp per replica (throughput: thousands of
                            replicas), 2 = one CTA per replica with batched conservative commit (latency: a few
                            trajectories; state resident in shared memory), 3 = the same batched commit with every round spread
@@ -170,11 +170,42 @@ int dmdb_get_replica_stats(dmdb_handle* h, int replica, dmdb_stats* s);
  * events / of which list rebuilds. */
 int dmdb_get_batch_stats(dmdb_handle* h, int replica, int64_t out[16]);
 
-/* Replica exchange (new functionality, no reference counterpart): gathers (E_pot, T*) of the local replicas.
- * The collective itself is done by the host language binding over NCCL (torch.distributed) -- see
- * INTEGRATION.md; the library computes the local potential energies and applies temperature swaps. */
+/* Replica exchange (new functionality: the reference runs its temp_0xx files one after the other by hand,
+ * qfile/script.sh:11-18; SURVEY.md 8b "dmdb_exchange(h, ncclComm_t)" and 8e).
+ *
+ * dmdb_exchange is one exchange step, entirely on the device and on the library's stream: energy.f reduction of the
+ * local replicas -> (E_pot, T*) -> ncclAllGather over the communicator -> the same Metropolis decision on every rank
+ * (dmd_exchange.h: ladders of `ladder_size` replicas cut from the slot order r * world + rank, temperature
+ * neighbours swap TEMPERATURES with probability min(1, exp((beta_a - beta_b)(E_a - E_b))), counter RNG shared by all
+ * ranks) -> velocities of the replicas whose temperature changed rescaled by sqrt(T_new/T_old), time constants reset
+ * (main.F90:143-156), lists + calendar rebuilt.  Nothing but the 16 bytes per replica of the gather crosses NVLink,
+ * and nothing comes back to the host except the counters below.
+ *   nccl_comm   an ncclComm_t the host created (a Fortran / C++ host linked against NCCL), or NULL: the communicator
+ *               of dmdb_comm_init, or no collective at all when the handle is the only rank.
+ *   ladder_size 2..32; 0 = one ladder over everything (at most 32 replicas).  Replicas beyond the last whole ladder
+ *               keep their temperature.
+ * dmdb_nccl_unique_id / dmdb_comm_init: create the communicator inside the library (rank 0 makes the id, the host
+ * broadcasts the 128 bytes by whatever means it has, every rank calls dmdb_comm_init).  NCCL is bound at run time
+ * (libnccl.so.2; the instance the host process has already loaded, if any).
+ * dmdb_exchange_gathered: the same decision + temperature change for a host that gathers (E_pot, T*) itself
+ * (MPI in a Fortran host, gloo in the CPU tests): `gathered` holds world x n_replicas x 2 doubles, rank-major. */
+typedef struct dmdb_exchange_stats {
+  int32_t ladders;        /* ladders in the gathered replica set */
+  int32_t attempted;      /* neighbour pairs that attempted a swap (all ranks) */
+  int32_t accepted;       /* ... and swapped */
+  int32_t changed_local;  /* local replicas whose temperature changed */
+  double device_ms;       /* CUDA-event time of the whole step on the library's stream */
+  int32_t kernel_launches;
+  int32_t reserved;
+} dmdb_exchange_stats;
+int dmdb_nccl_unique_id(char id[128]);
+int dmdb_comm_init(dmdb_handle* h, const char id[128], int world, int rank);
+int dmdb_exchange(dmdb_handle* h, void* nccl_comm, int64_t step, uint64_t seed, int32_t ladder_size, dmdb_exchange_stats* out);
+int dmdb_exchange_gathered(dmdb_handle* h, const double* gathered, int world, int rank, int64_t step, uint64_t seed,
+                           int32_t ladder_size, dmdb_exchange_stats* out);
+/* The pieces, for a host that wants to decide itself: potential energies of the local replicas ... */
 int dmdb_potential_energies(dmdb_handle* h, double* epot /* n_replicas */, double* tstar /* n_replicas */);
-/* Applies the outcome of an exchange: replicas whose entry differs from their current T* have their velocities
+/* ... and the temperature change: replicas whose entry differs from their current T* have their velocities
  * rescaled by sqrt(T_new/T_old), their time constants reset (main.F90:143-156) and lists + calendar rebuilt, all
  * on the device; H-bond state is kept.  Entries <= 0 leave the replica untouched. */
 int dmdb_apply_temperatures(dmdb_handle* h, const double* tstar_new /* n_replicas */);

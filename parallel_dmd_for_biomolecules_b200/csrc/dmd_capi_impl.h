@@ -38,6 +38,14 @@ struct dmdb_handle {
   double last_ms = 0;
   int last_launches = 0;
   int service_ctas = -1;  // dmdb_set_service_ctas
+  // replica exchange (dmdb_exchange): NCCL communicator of dmdb_comm_init (owned) and device scratch
+  void* comm = nullptr;
+  int world = 1, rank = 0;
+  double* xbuf = nullptr;
+  size_t xbuf_doubles = 0;
+  bool synced = false;  // dmdb_sync_positions has advanced every replica to true positions and nothing has run since
+  std::vector<dmd::RepScalars> sc_cache;  // the per-replica scalars as last downloaded (one D2H serves the error
+                                          // check and the tallies of a run)
 };
 
 namespace {
@@ -87,10 +95,11 @@ const char* device_error_text(int e) {
   return "unknown device error";
 }
 
-// after a device op: surface device-side error words
+// after a device op: surface device-side error words (downloads the per-replica scalars into h->sc_cache)
 int check_device_errors(dmdb_handle* h) {
   const int R = h->d.n_replicas;
-  std::vector<dmd::RepScalars> sc(R);
+  std::vector<dmd::RepScalars>& sc = h->sc_cache;
+  sc.resize(R);
   be::d2h(sc.data(), h->d.scal, sizeof(dmd::RepScalars) * R);
   for (int r = 0; r < R; r++)
     if (sc[r].error) {
@@ -134,6 +143,8 @@ int dmdb_create(const dmdb_params* p, const dmdb_topology* topo, const dmdb_tabl
     {
       const int ncc0 = (s.ncr + 1) >> 1;
       d.ncc3 = ncc0 * ncc0 * ncc0;
+      d.n_chains = s.nch[0] + (s.n_species == 2 ? s.nch[1] : 0);
+      d.chainwise = s.chainwise;
     }
     dmd::SysConst* dsys = dalloc<dmd::SysConst>(h.get(), 1);
     be::h2d(dsys, &s, sizeof(s));
@@ -208,6 +219,8 @@ void dmdb_destroy(dmdb_handle* h) {
   if (!h) return;
   for (void* q : h->allocs) be::release(q);
   if (h->pair_buf) be::release(h->pair_buf);
+  if (h->xbuf) be::release(h->xbuf);
+  if (h->comm) be::nccl_comm_destroy(h->comm);
   delete h;
 }
 
@@ -233,6 +246,7 @@ static void upload_replicas(dmdb_handle* h, int r0, int r1, const double* sv, si
   be::run_init(h->d, r0, (int)n, h->stage_sv, sv_stride, bptnr ? h->stage_bp : nullptr, bp_stride, h->temp_buf,
                h->model.params.seed);
   for (int r = r0; r < r1; r++) h->loaded[r] = 1;
+  h->synced = false;
 }
 
 int dmdb_set_state(dmdb_handle* h, int replica, const double* sv, const int32_t* bptnr) {
@@ -274,18 +288,23 @@ int dmdb_set_temperature(dmdb_handle* h, int replica, double tstar) {
     if (rc) return rc;
   }
   DMDB_TRY(h, {
-    // what a new `./dmd < temp_0xx` run does: true positions -> restart files -> start-up path
-    be::run_op(h->d, dmd::OP_SYNC_POS, r0, r1 - r0, 0, nullptr, nullptr, &h->last_ms, &h->last_launches);
-    const int N = h->model.sys.N;
-    std::vector<double> sv((size_t)N * 6);
-    std::vector<int32_t> bp(N);
-    for (int r = r0; r < r1; r++) {
-      int rc = dmdb_get_state(h, r, sv.data(), bp.data(), nullptr, nullptr, nullptr, nullptr, nullptr);
-      if (rc) return rc;
-      h->tstar[r] = tstar;
-      upload_replicas(h, r, r + 1, sv.data(), 0, bp.data(), 0);
+    // what a new `./dmd < temp_0xx` run does -- true positions (main.F90:1288-1295) -> restart files -> start-up path
+    // (inputinfo.f:76-101, main.F90:205-424) -- with the "files" staying on the device: the records are packed into
+    // the staging arrays the upload path uses (sv(6,N) + bptnr, the exact doubles config.f would write) and the run
+    // start reads them from there.  No host round trip.
+    const size_t N = (size_t)h->model.sys.N, R = (size_t)h->d.n_replicas;
+    if (!h->synced) be::run_op(h->d, dmd::OP_SYNC_POS, r0, r1 - r0, 0, nullptr, nullptr, &h->last_ms, &h->last_launches);
+    if (!h->stage_sv) {
+      h->stage_sv = dalloc<double>(h, R * N * 6);
+      h->stage_bp = dalloc<int32_t>(h, R * N);
     }
+    be::run_pack(h->d, h->stage_sv, h->stage_bp);
+    for (int r = r0; r < r1; r++) h->tstar[r] = tstar;
+    be::h2d(h->temp_buf, h->tstar.data(), R * sizeof(double));
+    be::run_init(h->d, r0, r1 - r0, h->stage_sv + (size_t)r0 * N * 6, N * 6, h->stage_bp + (size_t)r0 * N, N, h->temp_buf,
+                 h->model.params.seed);
     be::run_op(h->d, dmd::OP_START, r0, r1 - r0, 0, nullptr, nullptr, &h->last_ms, &h->last_launches);
+    if (r1 - r0 == h->d.n_replicas) h->synced = false;
   })
   return check_device_errors(h);
 }
@@ -325,6 +344,30 @@ int dmdb_device_fill(int device, int32_t* n_replicas, int32_t* n_service_ctas) {
   return DMDB_OK;
 }
 
+// dmdb_sync_positions leaves the beads at their true positions with the event clock unchanged (main.F90:1288-1295 is
+// the end of a run): the next thing must be a restart
+static const char* const SYNCED_MSG = "positions were advanced by dmdb_sync_positions: restart the run first (dmdb_set_state* or "
+                                      "dmdb_set_temperature)";
+
+static void stats_from_scalars(const dmdb_handle* h, const std::vector<dmd::RepScalars>& sc, int replica, dmdb_stats* s) {
+  const int R = (int)sc.size();
+  std::memset(s, 0, sizeof(*s));
+  for (int r = (replica < 0 ? 0 : replica); r < (replica < 0 ? R : replica + 1); r++) {
+    s->events += sc[r].coll;
+    for (int k = 0; k < 32; k++) {
+      s->nevents[k] += sc[r].nevents[k];
+      s->pair_events += sc[r].nevents[k];
+    }
+    s->ghosts += sc[r].numghosts;
+    s->updates += sc[r].nupdates - sc[r].nforcedupdate;
+    s->forced_updates += sc[r].nforcedupdate;
+    s->pair_predictions += sc[r].n_pair_pred;
+    s->nbr_visits += sc[r].n_nbr_visits;
+  }
+  s->device_ms = h->last_ms;
+  s->kernel_launches = h->last_launches;
+}
+
 static int run_impl(dmdb_handle* h, int64_t n_events, dmdb_stats* stats, int flags);
 int dmdb_run(dmdb_handle* h, int64_t n_events, dmdb_stats* stats) { return run_impl(h, n_events, stats, 0); }
 int dmdb_run_until_output(dmdb_handle* h, int64_t max_events, dmdb_stats* stats) { return run_impl(h, max_events, stats, 1); }
@@ -343,18 +386,21 @@ static int run_impl(dmdb_handle* h, int64_t n_events, dmdb_stats* stats, int fla
   if (engine == 2 && !be::block_engine_fits(h->model.sys)) engine = 1;
   const int op = engine == 3 ? dmd::OP_RUN_GRID : (engine == 2 ? dmd::OP_RUN_BLOCK : dmd::OP_RUN);
   const int svc_bits = op == dmd::OP_RUN ? ((h->service_ctas + 1) & 0xffff) << 8 : 0;  // run_op: bits 8-23 = 1 + service CTAs (0 = automatic)
+  if (h->synced) return fail(h, DMDB_ERR_STATE, SYNCED_MSG);
   DMDB_TRY(h, be::run_op(h->d, op, 0, h->d.n_replicas, n_events, nullptr, nullptr, &h->last_ms, &h->last_launches, flags | svc_bits);)
   rc = check_device_errors(h);
   if (rc) return rc;
-  if (stats) return dmdb_get_replica_stats(h, -1, stats);
+  if (stats) stats_from_scalars(h, h->sc_cache, -1, stats);  // the scalars just downloaded: no second copy
   return DMDB_OK;
 }
 
 int dmdb_sync_positions(dmdb_handle* h) {
   int rc = all_loaded(h);
   if (rc) return rc;
+  if (h->synced) return DMDB_OK;  // already at true positions: advancing twice would move the beads again
   DMDB_TRY(h, be::run_op(h->d, dmd::OP_SYNC_POS, 0, h->d.n_replicas, 0, nullptr, nullptr, &h->last_ms,
                          &h->last_launches);)
+  h->synced = true;
   return DMDB_OK;
 }
 
@@ -468,6 +514,7 @@ int dmdb_apply_temperatures(dmdb_handle* h, const double* tstar_new) {
   int rc = all_loaded(h);
   if (rc) return rc;
   if (!tstar_new) return fail(h, DMDB_ERR_ARG, "null argument");
+  if (h->synced) return fail(h, DMDB_ERR_STATE, SYNCED_MSG);
   const int R = h->d.n_replicas;
   DMDB_TRY(h, {
     std::vector<double> tn(R);
@@ -484,6 +531,84 @@ int dmdb_apply_temperatures(dmdb_handle* h, const double* tstar_new) {
     }
   })
   return check_device_errors(h);
+}
+
+// ---- replica exchange (new functionality)
+int dmdb_nccl_unique_id(char id[128]) {
+  if (!id) return fail(nullptr, DMDB_ERR_ARG, "null argument");
+  try {
+    be::nccl_unique_id(id);
+  } catch (const std::exception& e) {
+    return fail(nullptr, DMDB_ERR_CUDA, e.what());
+  }
+  return DMDB_OK;
+}
+
+int dmdb_comm_init(dmdb_handle* h, const char id[128], int world, int rank) {
+  if (!h || !id) return DMDB_ERR_ARG;
+  if (world < 1 || rank < 0 || rank >= world) return fail(h, DMDB_ERR_ARG, "dmdb_comm_init: need 0 <= rank < world");
+  DMDB_TRY(h, {
+    if (h->comm) be::nccl_comm_destroy(h->comm);
+    h->comm = nullptr;
+    if (world > 1) h->comm = be::nccl_comm_init(id, world, rank);
+    h->world = world;
+    h->rank = rank;
+  })
+  return DMDB_OK;
+}
+
+static int exchange_impl(dmdb_handle* h, void* comm, const double* gathered, int world, int rank, int64_t step, uint64_t seed,
+                         int32_t ladder_size, dmdb_exchange_stats* out) {
+  int rc = all_loaded(h);
+  if (rc) return rc;
+  if (h->synced) return fail(h, DMDB_ERR_STATE, SYNCED_MSG);
+  const int R = h->d.n_replicas;
+  if (world < 1 || rank < 0 || rank >= world) return fail(h, DMDB_ERR_ARG, "exchange: need 0 <= rank < world");
+  const long long M = (long long)world * R;
+  if (ladder_size <= 0) ladder_size = (int32_t)(M < dmd::XCH_MAX_LADDER ? M : dmd::XCH_MAX_LADDER);
+  if (ladder_size < 2 || ladder_size > dmd::XCH_MAX_LADDER) return fail(h, DMDB_ERR_ARG, "exchange: ladder size must be 2..32");
+  DMDB_TRY(h, {
+    const size_t need = 2 * (size_t)R + 3 * (size_t)M + 2 * (size_t)R + 8;
+    if (h->xbuf_doubles < need) {
+      if (h->xbuf) be::release(h->xbuf);
+      h->xbuf = (double*)be::alloc(need * sizeof(double));
+      h->xbuf_doubles = need;
+    }
+    dmd::XchCounts c;
+    std::memset(&c, 0, sizeof(c));
+    int launches = 0;
+    double ms = 0;
+    be::exchange(h->d, h->eout, h->xbuf, comm, gathered, world, rank, (long long)step, (unsigned long long)seed, ladder_size, &c,
+                 h->tstar.data(), &ms, &launches);
+    h->last_ms = ms;
+    h->last_launches = launches;
+    if (out) {
+      out->ladders = c.ladders; out->attempted = c.attempted; out->accepted = c.accepted; out->changed_local = c.changed_local;
+      out->device_ms = ms; out->kernel_launches = launches; out->reserved = 0;
+    }
+  })
+  return check_device_errors(h);
+}
+
+int dmdb_exchange(dmdb_handle* h, void* nccl_comm, int64_t step, uint64_t seed, int32_t ladder_size, dmdb_exchange_stats* out) {
+  if (!h) return DMDB_ERR_ARG;
+  int world = h->world, rank = h->rank;
+  void* comm = h->comm;
+  if (nccl_comm) {
+    try {
+      be::nccl_comm_geometry(nccl_comm, world, rank);
+    } catch (const std::exception& e) {
+      return fail(h, DMDB_ERR_CUDA, e.what());
+    }
+    comm = nccl_comm;
+  }
+  return exchange_impl(h, comm, nullptr, world, rank, step, seed, ladder_size, out);
+}
+
+int dmdb_exchange_gathered(dmdb_handle* h, const double* gathered, int world, int rank, int64_t step, uint64_t seed,
+                           int32_t ladder_size, dmdb_exchange_stats* out) {
+  if (!h || !gathered) return DMDB_ERR_ARG;
+  return exchange_impl(h, nullptr, gathered, world, rank, step, seed, ladder_size, out);
 }
 
 int dmdb_get_evcode(dmdb_handle* h, int replica, int n_pairs, const int32_t* i, const int32_t* j, int32_t* code) {
@@ -540,6 +665,7 @@ int dmdb_get_event_log(dmdb_handle* h, int replica, int64_t first, int64_t n, dm
   int rc = check_replica(h, replica, true);
   if (rc) return rc;
   static_assert(sizeof(dmdb_event) == sizeof(dmd::EventLogRec), "event record layout");
+  if (first < 0 || n < 0 || (n > 0 && !out)) return fail(h, DMDB_ERR_ARG, "event log: first and n must be >= 0");
   DMDB_TRY(h, {
     dmd::RepScalars sc;
     be::d2h(&sc, h->d.scal + replica, sizeof(sc));
@@ -578,23 +704,9 @@ int dmdb_get_replica_stats(dmdb_handle* h, int replica, dmdb_stats* s) {
   }
   DMDB_TRY(h, {
     const int R = h->d.n_replicas;
-    std::vector<dmd::RepScalars> sc(R);
-    be::d2h(sc.data(), h->d.scal, sizeof(dmd::RepScalars) * R);
-    std::memset(s, 0, sizeof(*s));
-    for (int r = (replica < 0 ? 0 : replica); r < (replica < 0 ? R : replica + 1); r++) {
-      s->events += sc[r].coll;
-      for (int k = 0; k < 32; k++) {
-        s->nevents[k] += sc[r].nevents[k];
-        s->pair_events += sc[r].nevents[k];
-      }
-      s->ghosts += sc[r].numghosts;
-      s->updates += sc[r].nupdates - sc[r].nforcedupdate;
-      s->forced_updates += sc[r].nforcedupdate;
-      s->pair_predictions += sc[r].n_pair_pred;
-      s->nbr_visits += sc[r].n_nbr_visits;
-    }
-    s->device_ms = h->last_ms;
-    s->kernel_launches = h->last_launches;
+    h->sc_cache.resize(R);
+    be::d2h(h->sc_cache.data(), h->d.scal, sizeof(dmd::RepScalars) * R);
+    stats_from_scalars(h, h->sc_cache, replica, s);
   })
   return DMDB_OK;
 }

@@ -16,6 +16,7 @@
 //   dmd_evcode_kernel        ev_code(i,j) read-back for the parity tests
 // There is no CPU fallback: be::init fails when no CUDA device is present.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <chrono>
 #include <cstddef>
@@ -64,6 +65,8 @@ namespace evl = w32;
     cudaError_t e_ = (x);                                                                            \
     if (e_ != cudaSuccess) throw std::runtime_error(std::string(#x) + ": " + cudaGetErrorString(e_)); \
   } while (0)
+
+#include "dmd_exchange.h"
 
 namespace dmd {
 
@@ -175,19 +178,42 @@ __device__ __noinline__ void svc_serve_in_kernel(DevArrays d, int r0, int nrep, 
     evl::Rep q;
     evl::rep_bind(q, d, tab, nullptr, rid);  // scalars as saved by the requesting warp (tfalse = 0, new interval_max)
     q.error = 0;
-    if (grid_fits) {
-      for (int k = tid; k < d.ncc3; k += nt) s_heads[k] = -1;
-      q.cellhead = s_heads;
-      q.cnext = s_cnext;
-      q.cpk = s_cpk;
+    // small systems: chain-wise candidate search (dmd_engine.h); its scratch -- packed cell coordinates, bounding
+    // spheres, near-chain masks -- lives in the group's share of the CTA's static shared memory
+    const int nch = d.n_chains;
+    const size_t cw_bytes = (size_t)d.n_beads * 4 + (size_t)nch * (sizeof(evl::ChainBound) + 8) + 32;
+    if (d.chainwise && cw_bytes <= scratch_bytes) {
+      evl::ChainBound* const cbound = reinterpret_cast<evl::ChainBound*>(scratch);
+      unsigned* const near = reinterpret_cast<unsigned*>(cbound + nch);
+      uint32_t* const cpk = near + 2 * nch;
+      for (int k = tid; k < 2 * nch; k += nt) near[k] = 0u;
+      evl::chainwise_cells(q, cpk, tid, nt);
+      evl::chainwise_bounds(q, cbound, nch, tid >> 5, nt >> 5);
       svc_group_sync(grp, gsz);
-    }
-    evl::cell_build(q, tid, nt);
-    svc_group_sync(grp, gsz);
-    evl::nbor_build(q, tid, nt);
-    if (!grid_fits) {
+      evl::chainwise_near(q, cbound, near, nch, tid, nt);
       svc_group_sync(grp, gsz);
-      evl::cell_clear(q, tid, nt);
+      const long long t1 = clock64();
+      evl::chainwise_lists(q, cpk, near, tid, nt);
+      svc_group_sync(grp, gsz);
+      if (tid == 0) {
+        atomicAdd(&d.svc_ctl[5], (unsigned long long)(t1 - t0));
+        atomicAdd(&d.svc_ctl[6], (unsigned long long)(clock64() - t1));
+      }
+    } else {
+      if (grid_fits) {
+        for (int k = tid; k < d.ncc3; k += nt) s_heads[k] = -1;
+        q.cellhead = s_heads;
+        q.cnext = s_cnext;
+        q.cpk = s_cpk;
+        svc_group_sync(grp, gsz);
+      }
+      evl::cell_build(q, tid, nt);
+      svc_group_sync(grp, gsz);
+      evl::nbor_build(q, tid, nt);
+      if (!grid_fits) {
+        svc_group_sync(grp, gsz);
+        evl::cell_clear(q, tid, nt);
+      }
     }
     for (int l = tid; l < q.N; l += nt) evl::redo_lane(q, l);  // events.f:23-107; the requester refreshes the group minima
     if (q.error && evl::Warp::lane() == 0 && atomicCAS(&q.sc->error, 0, q.error) == 0) q.sc->error_info = q.error_info;
@@ -688,12 +714,63 @@ __global__ void dmd_evcode_kernel(DevArrays d, int rid, int n_pairs, int32_t* bu
   buf[2 * n_pairs + k] = overlay_code(sc, i, rec[i], j, rec[j]);
 }
 
+
+// ---- replica exchange on the device (dmd_exchange.h): (E_pot, T*) of the local replicas, the decision for every
+// ladder of the gathered set, and the selection of the local replicas whose temperature changes
+__global__ void dmd_xch_pack_kernel(DevArrays d, const OutRec* eout, const double* tstar, double* local) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= d.n_replicas) return;
+  local[2 * r] = eout[r].ered - 0.5 * eout[r].sumvel;  // e_int of main.F90:358
+  local[2 * r + 1] = tstar[r];  // the T* the host set (setemp / 12 would not give back the same bits)
+}
+__global__ void dmd_xch_decide_kernel(const double* et, double* tnew, int n_ladders, int L, int world, int R, long long step,
+                                      unsigned long long seed, XchCounts* cnt) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  int att = 0, acc = 0;
+  if (l < n_ladders) xch_decide_ladder(et, tnew, l, L, world, R, step, seed, att, acc);
+  att = __reduce_add_sync(0xffffffffu, att);
+  acc = __reduce_add_sync(0xffffffffu, acc);
+  if ((threadIdx.x & 31) == 0 && att) {
+    atomicAdd(&cnt->attempted, att);
+    atomicAdd(&cnt->accepted, acc);
+  }
+}
+__global__ void dmd_xch_init_kernel(const double* et, double* tnew, int M, XchCounts* cnt, int n_ladders) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < M) tnew[g] = et[2 * g + 1];  // replicas outside every ladder keep their temperature
+  if (g == 0) {
+    cnt->attempted = cnt->accepted = cnt->changed_local = 0;
+    cnt->ladders = n_ladders;
+  }
+}
+__global__ void dmd_xch_select_kernel(const double* et, const double* tnew, int rank, int R, double* tsel, double* tcur, XchCounts* cnt) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  int ch = 0;
+  if (r < R) {
+    const int g = rank * R + r;
+    const double tn = tnew[g], to = et[2 * g + 1];
+    ch = tn != to;
+    tsel[r] = ch ? tn : 0.0;  // dmd_retemp_kernel: <= 0 leaves the replica untouched
+    tcur[r] = tn;
+  }
+  ch = __reduce_add_sync(0xffffffffu, ch);
+  if ((threadIdx.x & 31) == 0 && ch) atomicAdd(&cnt->changed_local, ch);
+}
+
 }  // namespace dmd
 
 namespace be {
 
+// One CUDA device per process (one process per GPU, like every multi-GPU path of this library): the stream, the timing
+// events and the whole-GPU engine's workspace below belong to that device.  A handle on a second device is refused
+// (init), and every entry point re-selects the device first (bind), so a host that changes the current device between
+// calls -- torch.cuda.set_device, another library -- cannot send our copies and launches elsewhere.
 static cudaStream_t g_stream = nullptr;
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+static int g_device = -1;
+inline void bind() {
+  if (g_device >= 0) cudaSetDevice(g_device);
+}
 
 inline bool init(int device, std::string& err) {
   int n = 0;
@@ -706,10 +783,16 @@ inline bool init(int device, std::string& err) {
     err = "CUDA device ordinal out of range";
     return false;
   }
+  if (g_device >= 0 && device != g_device) {
+    err = "this process already drives CUDA device " + std::to_string(g_device) + ": libdmdb200 uses one device per process "
+          "(start one process per GPU)";
+    return false;
+  }
   if ((e = cudaSetDevice(device)) != cudaSuccess) {
     err = cudaGetErrorString(e);
     return false;
   }
+  g_device = device;
   if (!g_stream) {
     cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking);
     cudaEventCreate(&g_ev0);
@@ -718,20 +801,26 @@ inline bool init(int device, std::string& err) {
   return true;
 }
 inline void* alloc(size_t n) {
+  bind();
   void* p = nullptr;
   CUDA_OK(cudaMalloc(&p, n ? n : 1));
   return p;
 }
 inline void release(void* p) { cudaFree(p); }
 inline void h2d(void* d, const void* h, size_t n) {
+  bind();
   CUDA_OK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, g_stream));
   CUDA_OK(cudaStreamSynchronize(g_stream));
 }
 inline void d2h(void* h, const void* d, size_t n) {
+  bind();
   CUDA_OK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, g_stream));
   CUDA_OK(cudaStreamSynchronize(g_stream));
 }
-inline void zero(void* d, size_t n) { CUDA_OK(cudaMemsetAsync(d, 0, n, g_stream)); }
+inline void zero(void* d, size_t n) {
+  bind();
+  CUDA_OK(cudaMemsetAsync(d, 0, n, g_stream));
+}
 inline void fill_i32(int32_t* d, int v, size_t n) {
   if (v == -1) CUDA_OK(cudaMemsetAsync(d, 0xff, n * 4, g_stream));
   else if (v == 0) CUDA_OK(cudaMemsetAsync(d, 0, n * 4, g_stream));
@@ -763,7 +852,7 @@ inline int sm_count() {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   return sms;
 }
-inline int default_service_ctas(int worker_ctas) { return worker_ctas >= 32 ? (worker_ctas * 10 + 26) / 52 : 0; }
+inline int default_service_ctas(int worker_ctas) { return worker_ctas >= 32 ? (worker_ctas * 10 + 32) / 64 : 0; }
 inline void device_fill(int& replicas, int& service) {
   const int sms = sm_count();
   int w = sms;
@@ -789,6 +878,7 @@ inline void launch_predict_all(const dmd::DevArrays& d, int r0, int nrep) {  // 
 inline void run_init(const dmd::DevArrays& d, int r0, int nrep, const double* sv, size_t sv_stride, const int32_t* bp,
                      size_t bp_stride, const double* tstar, unsigned long long seed0) {
   using namespace dmd;
+  bind();
   const int n = d.cal_stride > d.n_beads ? d.cal_stride : d.n_beads;
   dmd_bulk_reset_kernel<<<(nrep + 255) / 256, 256, 0, g_stream>>>(d, r0, nrep);
   dmd_bulk_init_kernel<<<bulk_grid(d, nrep, n), BULK_THREADS, 0, g_stream>>>(d, r0, sv, sv_stride, bp, bp_stride, tstar, seed0);
@@ -801,6 +891,7 @@ inline void run_init(const dmd::DevArrays& d, int r0, int nrep, const double* sv
   CUDA_OK(cudaStreamSynchronize(g_stream));
 }
 inline void run_pack(const dmd::DevArrays& d, double* sv, int32_t* bp) {
+  bind();
   dmd::dmd_pack_kernel<<<148 * 8, 256, 0, g_stream>>>(d, sv, bp);
   CUDA_OK(cudaGetLastError());
 }
@@ -916,6 +1007,7 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
   const int grid = (nrep + WARPS_PER_CTA - 1) / WARPS_PER_CTA;  // 32-lane kernels: one replica per hardware warp
   const int grid_evl = (nrep + EVL_RPC - 1) / EVL_RPC;          // event loop: DMD_EVL_W lanes per replica
   int nl = 1;
+  bind();
   CUDA_OK(cudaEventRecord(g_ev0, g_stream));
   switch (op) {
     case 0: launch_nbor(d, r0, nrep); launch_predict_all(d, r0, nrep); nl = 5; break;
@@ -975,9 +1067,11 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
       if (n_srv > 0 && getenv("DMDB_DEBUG")) {
         unsigned long long ctl[SVC_CTL_WORDS];
         d2h(ctl, d.svc_ctl, sizeof(ctl));
-        fprintf(stderr, "service: %d CTAs, %llu worker warps done, %llu rebuilds served, %.1f us each, %.1f ms busy per CTA; "
-                "%llu requests taken back, mean wait %.1f us\n", n_srv, ctl[0], ctl[1], ctl[1] ? (double)ctl[4] / ctl[1] / 1.9e3 : 0.0,
-                (double)ctl[4] / n_srv / 1.9e6, ctl[2], ctl[1] + ctl[2] ? (double)ctl[3] / (ctl[1] + ctl[2]) / 1.9e3 : 0.0);
+        fprintf(stderr, "service: %d CTAs, %llu worker warps done, %llu rebuilds served, %.1f us each (cells+bounds %.1f, lists %.1f), "
+                "%.1f ms busy per CTA; %llu requests taken back, mean wait %.1f us\n", n_srv, ctl[0], ctl[1],
+                ctl[1] ? (double)ctl[4] / ctl[1] / 1.9e3 : 0.0, ctl[1] ? (double)ctl[5] / ctl[1] / 1.9e3 : 0.0,
+                ctl[1] ? (double)ctl[6] / ctl[1] / 1.9e3 : 0.0, (double)ctl[4] / n_srv / 1.9e6, ctl[2],
+                ctl[1] + ctl[2] ? (double)ctl[3] / (ctl[1] + ctl[2]) / 1.9e3 : 0.0);
       }
       break;
     }
@@ -1001,6 +1095,121 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
   }
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaEventRecord(g_ev1, g_stream));
+  CUDA_OK(cudaStreamSynchronize(g_stream));
+  float t = 0;
+  CUDA_OK(cudaEventElapsedTime(&t, g_ev0, g_ev1));
+  if (ms) *ms = t;
+  if (launches) *launches = nl;
+}
+
+
+// ---- NCCL, bound at run time (no link-time dependency: a host that never exchanges needs no NCCL).  When the host
+// process already has NCCL loaded (torch.distributed, or a Fortran/C++ host linked against it), dlopen by soname
+// returns that very instance, so communicators created by the host can be passed in.
+namespace nccl {
+struct UniqueId {
+  char internal[128];
+};
+typedef int (*GetUniqueId_t)(UniqueId*);
+typedef int (*CommInitRank_t)(void**, int, UniqueId, int);
+typedef int (*CommDestroy_t)(void*);
+typedef int (*AllGather_t)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef const char* (*GetErrorString_t)(int);
+typedef int (*CommQuery_t)(void*, int*);
+static void* lib = nullptr;
+static GetUniqueId_t GetUniqueId = nullptr;
+static CommInitRank_t CommInitRank = nullptr;
+static CommDestroy_t CommDestroy = nullptr;
+static AllGather_t AllGather = nullptr;
+static GetErrorString_t GetErrorString = nullptr;
+static CommQuery_t CommCount = nullptr, CommUserRank = nullptr;
+constexpr int kDouble = 8;  // ncclFloat64
+inline void load() {
+  if (lib) return;
+  const char* names[] = {getenv("DMDB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    if (!n) continue;
+    lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  if (!lib) throw std::runtime_error("NCCL not found (libnccl.so.2; set DMDB_NCCL_LIB): replica exchange across GPUs needs it");
+  GetUniqueId = (GetUniqueId_t)dlsym(lib, "ncclGetUniqueId");
+  CommInitRank = (CommInitRank_t)dlsym(lib, "ncclCommInitRank");
+  CommDestroy = (CommDestroy_t)dlsym(lib, "ncclCommDestroy");
+  AllGather = (AllGather_t)dlsym(lib, "ncclAllGather");
+  GetErrorString = (GetErrorString_t)dlsym(lib, "ncclGetErrorString");
+  CommCount = (CommQuery_t)dlsym(lib, "ncclCommCount");
+  CommUserRank = (CommQuery_t)dlsym(lib, "ncclCommUserRank");
+  if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather) throw std::runtime_error("NCCL symbols missing");
+}
+inline void ok(int rc, const char* what) {
+  if (rc != 0) throw std::runtime_error(std::string(what) + ": " + (GetErrorString ? GetErrorString(rc) : "NCCL error"));
+}
+}  // namespace nccl
+inline void nccl_unique_id(char out[128]) {
+  nccl::load();
+  nccl::UniqueId id;
+  nccl::ok(nccl::GetUniqueId(&id), "ncclGetUniqueId");
+  std::memcpy(out, id.internal, 128);
+}
+inline void* nccl_comm_init(const char id128[128], int world, int rank) {
+  nccl::load();
+  nccl::UniqueId id;
+  std::memcpy(id.internal, id128, 128);
+  void* comm = nullptr;
+  nccl::ok(nccl::CommInitRank(&comm, world, id, rank), "ncclCommInitRank");
+  return comm;
+}
+inline void nccl_comm_geometry(void* comm, int& world, int& rank) {  // of a communicator the host created itself
+  nccl::load();
+  if (!nccl::CommCount || !nccl::CommUserRank) throw std::runtime_error("NCCL symbols missing");
+  nccl::ok(nccl::CommCount(comm, &world), "ncclCommCount");
+  nccl::ok(nccl::CommUserRank(comm, &rank), "ncclCommUserRank");
+}
+inline void nccl_comm_destroy(void* comm) {
+  if (comm && nccl::CommDestroy) nccl::CommDestroy(comm);
+}
+
+// One exchange step on the library's stream: energy kernel -> (E_pot, T*) -> all-gather (NCCL; or the host's own gather
+// passed in `gathered_host`) -> decision kernel -> retemp kernel for the local replicas whose temperature changed.
+// xb: device scratch [2R local | 2M gathered | M new temperatures | R selected | R current | XchCounts].
+inline void exchange(const dmd::DevArrays& d, dmd::OutRec* eout, double* xb, void* comm, const double* gathered_host, int world,
+                     int rank, long long step, unsigned long long seed, int L, dmd::XchCounts* counts_out, double* tstar_out,
+                     double* ms, int* launches) {
+  using namespace dmd;
+  bind();
+  const int R = d.n_replicas, M = world * R, n_ladders = M / L;
+  double* local = xb;
+  double* all = world > 1 ? xb + 2 * (size_t)R : local;
+  double* tnew = xb + 2 * (size_t)R + 2 * (size_t)M;
+  double* tsel = tnew + M;
+  double* tcur = tsel + R;
+  XchCounts* cnt = reinterpret_cast<XchCounts*>(tcur + R);
+  const int block = WARPS_PER_CTA * 32, grid = (R + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  CUDA_OK(cudaEventRecord(g_ev0, g_stream));
+  int nl = 0;
+  if (!gathered_host) {
+    CUDA_OK(cudaMemcpyAsync(tcur, tstar_out, sizeof(double) * R, cudaMemcpyHostToDevice, g_stream));  // current T* (in/out)
+    dmd_energy_kernel<<<grid, block, 0, g_stream>>>(d, 0, R, eout);
+    dmd_xch_pack_kernel<<<(R + 255) / 256, 256, 0, g_stream>>>(d, eout, tcur, local);
+    nl += 2;
+    if (world > 1) {
+      if (!comm) throw std::runtime_error("dmdb_exchange: more than one rank needs an NCCL communicator (dmdb_comm_init)");
+      nccl::load();
+      nccl::ok(nccl::AllGather(local, all, 2 * (size_t)R, nccl::kDouble, comm, g_stream), "ncclAllGather");
+    }
+  } else {
+    CUDA_OK(cudaMemcpyAsync(all, gathered_host, sizeof(double) * 2 * (size_t)M, cudaMemcpyHostToDevice, g_stream));
+  }
+  dmd_xch_init_kernel<<<(M + 255) / 256, 256, 0, g_stream>>>(all, tnew, M, cnt, n_ladders);
+  if (n_ladders > 0) dmd_xch_decide_kernel<<<(n_ladders + 127) / 128, 128, 0, g_stream>>>(all, tnew, n_ladders, L, world, R, step, seed, cnt);
+  dmd_xch_select_kernel<<<(R + 255) / 256, 256, 0, g_stream>>>(all, tnew, rank, R, tsel, tcur, cnt);
+  dmd_retemp_kernel<<<grid, block, 0, g_stream>>>(d, 0, R, tsel);
+  nl += 4;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(g_ev1, g_stream));
+  CUDA_OK(cudaMemcpyAsync(counts_out, cnt, sizeof(XchCounts), cudaMemcpyDeviceToHost, g_stream));
+  CUDA_OK(cudaMemcpyAsync(tstar_out, tcur, sizeof(double) * R, cudaMemcpyDeviceToHost, g_stream));
   CUDA_OK(cudaStreamSynchronize(g_stream));
   float t = 0;
   CUDA_OK(cudaEventElapsedTime(&t, g_ev0, g_ev1));

@@ -1240,6 +1240,176 @@ DMD_DEV void nbor(Rep& r) {  // nbor.f:33-137
 }
 
 #if !defined(DMD_HOST_TRACE)
+// ---------------------------------------------------------------------------------------------------------
+// Chain-wise list rebuild (service CTAs, small systems: SysConst.chainwise).  The cell walk above makes the lanes
+// of a warp chase different linked lists (measured: ~530 warp instructions per bead for ~15 candidates).  Here a
+// bead's candidates are the beads of its own chain plus the beads of the chains whose bounding sphere comes within
+// the largest list cut-off of its chain's sphere -- loops over contiguous index ranges that the lanes of a warp
+// (32 consecutive beads, i.e. one or two chains) run in step.  The neighbour SETS are the reference's:
+//   same chain     found in the 5 x 5 x 5 fine-cell block (cell_add.f:22 coordinates), then class rule nbor.f:60 /
+//                  distance rule nbor.f:97-105 -- as in nbor_build()
+//   other chains   classes 1 / 15 / 16 only (never bonded): distance rule; r <= rl <= 2 cell widths puts the pair
+//                  inside the block, the block test is kept as a cheap integer pre-filter.  The cut-off of a class-1
+//                  pair does not depend on its 40 / 50 overlay (SysConst.chainwise is set only if rlsq agrees)
+// and a pair closer than rl_max has sphere centres closer than R_a + R_b + rl_max for ANY periodic image.
+// Entry order (own chain ascending, then chains ascending) is deterministic.
+// ---------------------------------------------------------------------------------------------------------
+struct ChainBound {
+  double cx, cy, cz, rad;
+};
+constexpr uint32_t CPK_OUT = 0xffffffffu;  // bead outside the cell grid: the reference never looks it up
+DMD_DEV int chain_first(const SysConst& s, int c) { return c < s.nch[0] ? c * s.numbeads[0] : s.nop1 + (c - s.nch[0]) * s.numbeads[1]; }
+DMD_DEV int chain_len(const SysConst& s, int c) { return c < s.nch[0] ? s.numbeads[0] : s.numbeads[1]; }
+
+// step 1 (thread per bead): reference cell id + packed fine cell coordinates
+DMD_DEV void chainwise_cells(Rep& r, uint32_t* cpk, int tid, int nt) {
+  const SysConst& s = *r.c.sys;
+  const int ncr = s.ncr, nc = s.num_cell, nw = s.n_wrap;
+  for (int k = tid; k < r.N; k += nt) {
+    int cx, cy, cz;
+    (cell_coords)(s, r.rec[k], cx, cy, cz);
+    r.cellof[k] = 1 + (cx + nw) + (cy + nw) * nc + (cz + nw) * nc * nc;  // cell_add.f:25
+    const bool out = cx < 0 || cy < 0 || cz < 0 || cx >= ncr || cy >= ncr || cz >= ncr;
+    cpk[k] = out ? CPK_OUT : cpk_pack(cx, cy, cz);
+  }
+}
+// step 2 (hardware warp per chain): bounding sphere around the mean bead position (minimum image to the first bead)
+DMD_DEV void chainwise_bounds(const Rep& r, ChainBound* cb, int nch, int warp, int nwarps) {
+  const SysConst& s = *r.c.sys;
+  const int hl = threadIdx.x & 31;
+  for (int c = warp; c < nch; c += nwarps) {
+    const int f = (chain_first)(s, c), nb = (chain_len)(s, c);
+    const BeadRec* p0 = &r.rec[f];
+    const double x0 = p0->x, y0 = p0->y, z0 = p0->z;
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (int j = hl; j < nb; j += 32) {
+      const BeadRec* p = &r.rec[f + j];
+      double dx = p->x - x0, dy = p->y - y0, dz = p->z - z0;
+      sx += dx - dmd_round(dx); sy += dy - dmd_round(dy); sz += dz - dmd_round(dz);
+    }
+    for (int m = 16; m >= 1; m >>= 1) {
+      sx += __shfl_xor_sync(0xffffffffu, sx, m);
+      sy += __shfl_xor_sync(0xffffffffu, sy, m);
+      sz += __shfl_xor_sync(0xffffffffu, sz, m);
+    }
+    const double cx = x0 + sx / nb, cy = y0 + sy / nb, cz = z0 + sz / nb;
+    double rad = 0.0;
+    for (int j = hl; j < nb; j += 32) {
+      const BeadRec* p = &r.rec[f + j];
+      double dx = p->x - cx, dy = p->y - cy, dz = p->z - cz;
+      dx -= dmd_round(dx); dy -= dmd_round(dy); dz -= dmd_round(dz);
+      const double d = dmd_sqrt(dx * dx + dy * dy + dz * dz);
+      rad = d > rad ? d : rad;
+    }
+    for (int m = 16; m >= 1; m >>= 1) {
+      const double o = __shfl_xor_sync(0xffffffffu, rad, m);
+      rad = o > rad ? o : rad;
+    }
+    if (hl == 0) {
+      ChainBound b;
+      b.cx = cx; b.cy = cy; b.cz = cz; b.rad = rad;
+      cb[c] = b;
+    }
+  }
+}
+// step 3 (thread per ordered chain pair): near[a] bit b <=> the spheres come within the largest list cut-off
+DMD_DEV void chainwise_near(const Rep& r, const ChainBound* cb, unsigned* near, int nch, int tid, int nt) {
+  const double reach = r.c.sys->rl_max * (1.0 + 1e-9) + 1e-12;
+  for (int p = tid; p < nch * nch; p += nt) {
+    const int a = p / nch, b = p - a * nch;
+    if (a == b) continue;
+    const ChainBound A = cb[a], B = cb[b];
+    double dx = A.cx - B.cx, dy = A.cy - B.cy, dz = A.cz - B.cz;
+    dx -= dmd_round(dx); dy -= dmd_round(dy); dz -= dmd_round(dz);
+    const double lim = A.rad + B.rad + reach;
+    if (dx * dx + dy * dy + dz * dz <= lim * lim) atomicOr(&near[2 * a + (b >> 5)], 1u << (b & 31));
+  }
+}
+// step 4 (thread per bead; whole hardware warps): the two lists of every bead
+DMD_DEV void chainwise_lists(Rep& r, const uint32_t* cpk, const unsigned* near, int tid, int nt) {
+  const SysConst& s = *r.c.sys;
+  const int cap = r.cap, ncr = s.ncr;
+  int overflow = 0;
+  for (int base = 0; base < r.N; base += nt) {  // the same trip count for every lane of a hardware warp
+    const int k = base + tid;
+    const bool valid = k < r.N;
+    const int kk = valid ? k : 0;
+    const BeadRec rk = r.rec[kk];
+    const uint32_t mk = r.c.meta[kk];
+    const int ck = r.c.chain[kk];
+    const uint32_t pk = cpk[kk];
+    const bool live = valid && pk != CPK_OUT;
+    int nu = 0, nd = 0;
+    auto append = [&](int j, int sc) {
+      const uint32_t e = ((uint32_t)sc << NB_SHIFT) | (uint32_t)j;
+      if (j > k) {
+        if (nu < cap) r.up[(size_t)k * cap + nu] = e;
+        nu++;
+      } else {
+        if (nd < cap) r.dn[(size_t)k * cap + nd] = e;
+        nd++;
+      }
+    };
+    auto within = [&](int j, int sc) {  // nbor.f:97-105 with the cut-off of the static class
+      const BeadRec* pj = &r.rec[j];
+      double rx = rk.x - pj->x, ry = rk.y - pj->y, rz = rk.z - pj->z;
+      rx = rx - dmd_round(rx);
+      ry = ry - dmd_round(ry);
+      rz = rz - dmd_round(rz);
+      return rx * rx + ry * ry + rz * rz <= s.rlsq[sc];
+    };
+    // (a) own chain
+    {
+      const int sp = meta_sp(mk), nb = s.numbeads[sp];
+      const int own_lo = kk - meta_local(mk);
+      const uint8_t* const sct_row = r.c.sctab + s.sct_off[sp] + (size_t)meta_local(mk) * nb;
+      const int nbmax = s.numbeads[0] > s.numbeads[1] ? s.numbeads[0] : s.numbeads[1];
+      for (int lj = 0; lj < nbmax; lj++) {
+        const int j = own_lo + lj;
+        if (!live || lj >= nb || j == k) continue;
+        const uint32_t pj = cpk[j];
+        if (pj == CPK_OUT || !in_fine_stencil(pk, pj, ncr)) continue;
+        const int sc = (int)sct_row[lj];
+        if (code_is_bonded_class(sc) || within(j, sc)) append(j, sc);  // nbor.f:60 / :97-105
+      }
+    }
+    // (b) the chains near the own one: the union over the hardware warp keeps the loops in step
+    unsigned m0 = live ? near[2 * ck] : 0u, m1 = live ? near[2 * ck + 1] : 0u;
+    unsigned u0 = __reduce_or_sync(0xffffffffu, m0), u1 = __reduce_or_sync(0xffffffffu, m1);
+    for (int half = 0; half < 2; half++) {
+      unsigned u = half ? u1 : u0;
+      const unsigned mine_mask = half ? m1 : m0;
+      while (u) {
+        const int bit = __ffs((int)u) - 1;
+        u &= u - 1;
+        const int c = half * 32 + bit;
+        const bool mine = (mine_mask >> bit) & 1u;
+        const int f = (chain_first)(s, c), nb = (chain_len)(s, c);
+        for (int lj = 0; lj < nb; lj++) {
+          const int j = f + lj;
+          if (!mine) continue;
+          const uint32_t pj = cpk[j];
+          if (pj == CPK_OUT || !in_fine_stencil(pk, pj, ncr)) continue;
+          const int sc = static_code(s, mk, ck, k, r.c.meta[j], c, j);  // other chain: 1, 15 or 16
+          if (within(j, sc)) append(j, sc);
+        }
+      }
+    }
+    if (valid) {
+      if (nu > cap || nd > cap) {
+        overflow = nu > nd ? nu : nd;
+        nu = nu > cap ? cap : nu;
+        nd = nd > cap ? cap : nd;
+      }
+      r.nup[k] = (uint16_t)nu;
+      r.ndn[k] = (uint16_t)nd;
+    }
+  }
+  if (overflow) {  // reported through the stored scalars (the service CTA has no replica view of its own)
+    if (atomicCAS(&r.sc->error, 0, DMD_E_NBR_CAP) == 0) r.sc->error_info = overflow;
+  }
+}
+
 // ---- list-rebuild service (device only).  A warp whose replica needs nbor() + events() publishes the request
 // in its svc word and sleeps; a service CTA on another SM claims it (1 -> 2), rebuilds with all its threads and
 // clears the word.  release/acquire at gpu scope on the word orders the replica's arrays between the two SMs (the
@@ -1293,8 +1463,9 @@ DMD_COLD bool svc_request(Rep r) {
       atomicAdd(&r.svc_ctl[3], (unsigned long long)(clock64() - t0));
     }
   }
+  Warp::sync();  // a memory-ordering point for all lanes: they read the arrays the service CTA wrote after lane 0's acquire
   res = Warp::shfl(res, 0);
-  if (res == 2) {
+  if (res == 2) {  // time-out while being served: the service CTA may still be writing -- report it, touch nothing else
     if (Warp::lane() == 0) {
       r.sc->error = DMD_E_SERVICE;
       r.sc->error_info = 0;

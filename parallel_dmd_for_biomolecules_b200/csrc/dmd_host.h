@@ -244,6 +244,20 @@ inline void build_model(const dmdb_params& p, const dmdb_topology& topo, const d
     s.rlsq[i] = 0.0;
     if (sig_max[i] != 0.0) s.rlsq[i] = hsq((rl_const - 1) * sig_max_all + sig_max[i]);
   }
+  {  // the chain-wise list rebuild of the service CTAs (dmd_engine.h, nbor_chainwise): its pair test uses the static
+     // class only, which is exact when the overlay codes 40..50 share the cut-off of code 1
+    double rm = 0.0;
+    bool same = true;
+    for (int i = 1; i <= 50; i++) {
+      if (s.rlsq[i] > rm) rm = s.rlsq[i];
+      if (i >= 40 && s.rlsq[i] != s.rlsq[1]) same = false;
+    }
+    s.rl_max = std::sqrt(rm);
+    const int nchains = s.nch[0] + (topo.n_species == 2 ? s.nch[1] : 0);
+    const bool short_chains = s.numbeads[0] <= 64 && (topo.n_species < 2 || s.numbeads[1] <= 64);
+    s.chainwise = (same && nchains <= 64 && short_chains && s.sct_off[0] >= 0 && (topo.n_species < 2 || s.nch[1] == 0 || s.sct_off[1] >= 0)) ? 1 : 0;
+    s.pad_cw = 0;
+  }
   const double rl = rl_const * sig_max_all;
   s.hdelr = hsq(0.4 * (rl - sig_max_all));
   s.sig_max_all = sig_max_all;

@@ -103,6 +103,9 @@ struct SysConst {
   double eps1;               // epsilon(1)
   double eps_hb;             // ep_sqrt(5,8), energy.f:74
   double hdelr, width, half, sig_max_all, boxl_orig;
+  double rl_max;             // largest list cut-off, sqrt(max rlsq): reach of the chain-wise list rebuild
+  int32_t chainwise;         // 1: the chain-wise list rebuild applies (<= 64 chains of <= 64 beads, rlsq(40..50) == rlsq(1))
+  int32_t pad_cw;
   double shlddia_sq[784];    // copies of PairTables.shlddia_sq / ep_sqrt (cold: shoulder events, well depths, energy)
   double ep_sqrt[784];
   // per-residue side-chain bond limits, already multiplied out like bond.f:82-91:
@@ -192,6 +195,8 @@ struct DevArrays {
   // constant bank, so a replica's array bases can be recomputed instead of being held (or spilled) in registers
   int32_t cap, ngroups, log_cap, out_cap;
   int32_t ncc3;           // coarse cells per replica (entries of cellhead)
+  int32_t n_chains;       // chains over both species
+  int32_t chainwise;      // copy of SysConst.chainwise
   // list-rebuild service of the warp-per-replica engine (dmd_cuda.cu: a few CTAs of the event-loop kernel do the
   // neighbour-list + calendar rebuilds for the warps of all other CTAs, so that the event-loop SMs keep only the
   // hot loop in their 32 KB instruction caches)

@@ -28,8 +28,15 @@ SYMBOLS = [
     "dmdb_get_nbors", "dmdb_get_calendar", "dmdb_get_state", "dmdb_get_evcode", "dmdb_energy_of",
     "dmdb_get_event_log", "dmdb_get_replica_stats", "dmdb_potential_energies", "dmdb_set_state_all",
     "dmdb_get_state_all", "dmdb_apply_temperatures", "dmdb_get_batch_stats", "dmdb_run_until_output",
-    "dmdb_device_fill", "dmdb_set_service_ctas",
+    "dmdb_device_fill", "dmdb_set_service_ctas", "dmdb_nccl_unique_id", "dmdb_comm_init", "dmdb_exchange",
+    "dmdb_exchange_gathered",
 ]
+
+
+class ExchangeStats(C.Structure):
+    """dmdb_exchange_stats"""
+    _fields_ = [("ladders", C.c_int32), ("attempted", C.c_int32), ("accepted", C.c_int32), ("changed_local", C.c_int32),
+                ("device_ms", C.c_double), ("kernel_launches", C.c_int32), ("reserved", C.c_int32)]
 
 
 def device_fill(device: int = 0, lib_path: Optional[str] = None):
@@ -133,6 +140,37 @@ class DMD:
         t = np.ascontiguousarray(tstar_new, dtype=np.float64)
         assert t.shape == (self.n_replicas,)
         self._chk(self._l.dmdb_apply_temperatures(self._h, _p(t, C.c_double)))
+
+    # -- replica exchange (dmdb_exchange: energies, NCCL all-gather, decision and temperature change on the device) ----
+    def comm_init(self, world: int, rank: int, broadcast=None):
+        """create the NCCL communicator inside the library.  `broadcast(bytes_or_None) -> bytes` must return rank 0's
+        128-byte id on every rank (e.g. torch.distributed.broadcast_object_list); world == 1 needs none."""
+        buf = (C.c_char * 128)()
+        if world > 1:
+            if rank == 0:
+                rc = self._l.dmdb_nccl_unique_id(buf)
+                if rc != 0:
+                    raise DMDError(rc, (self._l.dmdb_last_error(None) or b"").decode())
+            data = broadcast(bytes(buf.raw) if rank == 0 else None)
+            buf = (C.c_char * 128).from_buffer_copy(data)
+        self._chk(self._l.dmdb_comm_init(self._h, buf, int(world), int(rank)))
+
+    def exchange(self, step: int, seed: int = 12345, ladder_size: int = 0, nccl_comm: Optional[int] = None) -> ExchangeStats:
+        """one exchange step over the communicator of comm_init (or `nccl_comm`, an ncclComm_t as integer)"""
+        st = ExchangeStats()
+        self._chk(self._l.dmdb_exchange(self._h, C.c_void_p(nccl_comm), C.c_int64(step), C.c_uint64(seed),
+                                        C.c_int32(ladder_size), C.byref(st)))
+        return st
+
+    def exchange_gathered(self, gathered: np.ndarray, world: int, rank: int, step: int, seed: int = 12345,
+                          ladder_size: int = 0) -> ExchangeStats:
+        """the same decision + temperature change from (E_pot, T*) the host gathered itself: (world * R, 2) float64"""
+        g = np.ascontiguousarray(gathered, dtype=np.float64)
+        assert g.shape == (world * self.n_replicas, 2)
+        st = ExchangeStats()
+        self._chk(self._l.dmdb_exchange_gathered(self._h, _p(g, C.c_double), int(world), int(rank), C.c_int64(step),
+                                                 C.c_uint64(seed), C.c_int32(ladder_size), C.byref(st)))
+        return st
 
     def set_temperature(self, tstar: float, replica: int = -1):
         self._chk(self._l.dmdb_set_temperature(self._h, replica, C.c_double(tstar)))

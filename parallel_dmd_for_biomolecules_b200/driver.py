@@ -118,6 +118,58 @@ class RunFiles:
         fileio.write_lastvel(self.path(self.run, "lastvel"), coll, vel.T)
 
 
+def _run_on_handle(d: DMD, files: RunFiles, topo: Topology, tstar: float, ncoll: int, boxl: float) -> dict:
+    """the body of one ``./dmd < temp_0xx`` run on a handle whose state has just been (re)started at ``tstar``:
+    first .energy line (main.F90:347-378), the event loop with a record at every output pseudo-event
+    (main.F90:1191-1246), the wrap-up records and the final PDB (main.F90:1288-1346)"""
+    setemp = 12.0 * tstar
+    period = 3.3 / math.sqrt(setemp) + 5.0  # main.F90:1244
+    N = topo.n_beads
+    lines = 0
+
+    def observables():
+        st = d.state(0)
+        true_xyz = st["sv"][:, :3] + st["sv"][:, 3:] * st["tfalse"]  # config.f:19-23
+        e = d.energy(0)
+        rg, e2e = radgyr(topo, true_xyz, boxl), end_to_end(topo, true_xyz, boxl)
+        return st, true_xyz, e, rg, e2e
+
+    st, xyz, e, rg, e2e = observables()
+    files.energy_line(fileio.energy_line(0, 0.0, e.ered, e.tred, e.hb_alpha, e.hb_ii, e.hb_ij, e.ehh_ii, e.ehh_ij, rg, e2e))
+    lines += 1
+    done = 0
+    while done < ncoll:
+        d.run_until_output(ncoll - done)
+        st = d.state(0)
+        done = st["coll"]
+        # did the replica stop right after an output pseudo-event?  That event re-arms itself one period after its own
+        # time (main.F90:1244), and tfalse moves on with every later event -- so the test also holds when the output
+        # event was the very last event of the budget.
+        tim = d.calendar(0)[0]
+        if abs((tim[N + 2] - st["tfalse"]) - period) < 1e-9:
+            st, xyz, e, rg, e2e = observables()
+            tred_time = (st["t"] + st["tfalse"]) * math.sqrt(setemp) / SIGMA_N
+            files.energy_line(fileio.energy_line(done, tred_time, e.ered, e.tred, e.hb_alpha, e.hb_ii, e.hb_ij,
+                                                 e.ehh_ii, e.ehh_ij, rg, e2e))
+            files.config(done, st["t"] + st["tfalse"], xyz, st["sv"][:, 3:], st["bptnr"])
+            lines += 1
+    # wrap-up, main.F90:1288-1330: true positions, wrapped; final line and records
+    d.sync_positions()
+    st = d.state(0)
+    xyz = st["sv"][:, :3]
+    e = d.energy(0)
+    rg, e2e = radgyr(topo, xyz, boxl), end_to_end(topo, xyz, boxl)
+    t_end = st["t"] + st["tfalse"]
+    files.energy_line(fileio.energy_line(done - 1, t_end * math.sqrt(setemp) / SIGMA_N, e.ered, e.tred, e.hb_alpha,
+                                         e.hb_ii, e.hb_ij, e.ehh_ii, e.ehh_ij, rg, e2e))
+    files.config(done, t_end, xyz, st["sv"][:, 3:], st["bptnr"])
+    lines += 1
+    fileio.write_pdb(files.path(files.run, "pdb"), topo, xyz * boxl)  # after scale_up.f: Angstrom
+    stats = d.stats(0)
+    return dict(run=files.run, energy_lines=lines, events=done, ered=e.ered, tred=e.tred, hb=e.hb_ii + e.hb_ij,
+                ghosts=stats.ghosts, updates=stats.updates + stats.forced_updates)
+
+
 def run_temperature(workdir: str, topo: Topology, tables: Tables, tstar: float, ncoll: int, boxl: float = 158.54,
                     canon: bool = True, seed: int = 1058472402, engine: int = 0, lib_path: Optional[str] = None,
                     device: int = 0) -> dict:
@@ -127,58 +179,44 @@ def run_temperature(workdir: str, topo: Topology, tables: Tables, tstar: float, 
     sv, bp = files.restart(topo.n_beads)
     fileio.write_rca(files.path(files.prev, "rca"), topo, tables, sv[:, :3], boxl)
     p = make_params(boxl=boxl, tstar=tstar, canon=canon, n_replicas=1, device=device, seed=seed, engine=engine)
-    setemp = 12.0 * tstar
-    lines = 0
-
-    def observables(d: DMD):
-        st = d.state(0)
-        true_xyz = st["sv"][:, :3] + st["sv"][:, 3:] * st["tfalse"]  # config.f:19-23
-        e = d.energy(0)
-        rg, e2e = radgyr(topo, true_xyz, boxl), end_to_end(topo, true_xyz, boxl)
-        return st, true_xyz, e, rg, e2e
-
     with DMD(p, topo, tables, lib_path=lib_path) as d:
         d.set_state(sv, bp)
-        st, xyz, e, rg, e2e = observables(d)
-        files.energy_line(fileio.energy_line(0, 0.0, e.ered, e.tred, e.hb_alpha, e.hb_ii, e.hb_ij, e.ehh_ii, e.ehh_ij, rg, e2e))
-        lines += 1
-        done = 0
-        while done < ncoll:
-            budget = ncoll - done
-            d.run_until_output(budget)
-            st = d.state(0)
-            # fewer events than asked for: the replica stopped right after an output pseudo-event.  (An output event
-            # that is exactly the last event of the budget is covered by the wrap-up record below.)
-            stopped_at_output = st["coll"] - done < budget
-            done = st["coll"]
-            if stopped_at_output:
-                st, xyz, e, rg, e2e = observables(d)
-                tred_time = (st["t"] + st["tfalse"]) * math.sqrt(setemp) / SIGMA_N
-                files.energy_line(fileio.energy_line(done, tred_time, e.ered, e.tred, e.hb_alpha, e.hb_ii, e.hb_ij,
-                                                     e.ehh_ii, e.ehh_ij, rg, e2e))
-                files.config(done, st["t"] + st["tfalse"], xyz, st["sv"][:, 3:], st["bptnr"])
-                lines += 1
-        # wrap-up, main.F90:1288-1330: true positions, wrapped; final line and records
-        d.sync_positions()
-        st = d.state(0)
-        xyz = st["sv"][:, :3]
-        e = d.energy(0)
-        rg, e2e = radgyr(topo, xyz, boxl), end_to_end(topo, xyz, boxl)
-        t_end = st["t"] + st["tfalse"]
-        files.energy_line(fileio.energy_line(done - 1, t_end * math.sqrt(setemp) / SIGMA_N, e.ered, e.tred, e.hb_alpha,
-                                             e.hb_ii, e.hb_ij, e.ehh_ii, e.ehh_ij, rg, e2e))
-        files.config(done, t_end, xyz, st["sv"][:, 3:], st["bptnr"])
-        lines += 1
-        fileio.write_pdb(files.path(files.run, "pdb"), topo, xyz * boxl)  # after scale_up.f: Angstrom
-        stats = d.stats(0)
-    return dict(run=files.run, energy_lines=lines, events=done, ered=e.ered, tred=e.tred, hb=e.hb_ii + e.hb_ij,
-                ghosts=stats.ghosts, updates=stats.updates + stats.forced_updates)
+        return _run_on_handle(d, files, topo, tstar, ncoll, boxl)
 
 
-def anneal(workdir: str, topo: Topology, tables: Tables, schedule: Sequence[Sequence[float]], **kw) -> List[dict]:
-    """qfile/script.sh:11-18: ``for t in 050 045 ... 022: ./dmd < temp_$t`` then the long run at 0.18 -- one
-    run_temperature call per (T*, ncoll) pair, each restarting from the files the previous one wrote."""
-    return [run_temperature(workdir, topo, tables, float(t), int(n), **kw) for t, n in schedule]
+def anneal(workdir: str, topo: Topology, tables: Tables, schedule: Sequence[Sequence[float]], resident: bool = True,
+           boxl: float = 158.54, canon: bool = True, seed: int = 1058472402, engine: int = 0,
+           lib_path: Optional[str] = None, device: int = 0) -> List[dict]:
+    """qfile/script.sh:11-18: ``for t in 050 045 ... 022: ./dmd < temp_$t`` then the long run at 0.18.
+
+    resident=True (default): ONE handle for the whole schedule.  The first run restarts from the files in ``workdir``;
+    every later run starts from the state resident on the device -- ``dmdb_set_temperature`` does on the device what
+    the reference does through its restart files (true positions, wrap, start-up path with the new T*, RNG re-seeded)
+    -- so the per-temperature host round trip is gone while every runNNNN.* file is byte-identical to the chained runs.
+    resident=False: one run_temperature call per (T*, ncoll) pair, each restarting from the files of the previous."""
+    kw = dict(boxl=boxl, canon=canon, seed=seed, engine=engine, lib_path=lib_path, device=device)
+    if not resident:
+        return [run_temperature(workdir, topo, tables, float(t), int(n), **kw) for t, n in schedule]
+    out = []
+    d = None
+    try:
+        for k, (t, n) in enumerate(schedule):
+            files = RunFiles(workdir)
+            if d is None:
+                sv, bp = files.restart(topo.n_beads)
+                p = make_params(boxl=boxl, tstar=float(t), canon=canon, n_replicas=1, device=device, seed=seed, engine=engine)
+                d = DMD(p, topo, tables, lib_path=lib_path)
+                d.set_state(sv, bp)
+                start_xyz = sv[:, :3]
+            else:
+                d.set_temperature(float(t))  # restart on resident state
+                start_xyz = d.state(0)["sv"][:, :3]
+            fileio.write_rca(files.path(files.prev, "rca"), topo, tables, start_xyz, boxl)
+            out.append(_run_on_handle(d, files, topo, float(t), int(n), boxl))
+    finally:
+        if d is not None:
+            d.close()
+    return out
 
 
 def schedule_from_temp_files(root: str, names: Sequence[str]) -> List[List[float]]:

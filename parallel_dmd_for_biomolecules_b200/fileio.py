@@ -16,6 +16,8 @@ def _records(path: str) -> Iterator[bytes]:
     off = 0
     while off + 4 <= len(data):
         (n,) = struct.unpack_from("<i", data, off)
+        if n < 0 or off + 8 + n > len(data):
+            break  # a record cut short (run killed inside config()): keep what is complete, like `read(7,end=120)`
         body = data[off + 4: off + 4 + n]
         (n2,) = struct.unpack_from("<i", data, off + 4 + n)
         if n2 != n:

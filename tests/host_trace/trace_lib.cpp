@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../parallel_dmd_for_biomolecules_b200/csrc/dmd_block.h"  // includes dmd_engine.h (no include guard: once)
+#include "../../parallel_dmd_for_biomolecules_b200/csrc/dmd_exchange.h"
 #include "../../parallel_dmd_for_biomolecules_b200/csrc/dmd_types.h"
 
 // The CTA-per-replica engine (dmd_block.h) is emulated with one host thread per (1-lane) virtual warp; its
@@ -153,6 +154,45 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
       }
     }
   }
+  if (ms) *ms = 0;
+  if (launches) *launches = 0;
+}
+// replica exchange: the same decision code (dmd_exchange.h) on the CPU; more than one rank needs the host's own gather
+inline void nccl_unique_id(char*) { throw std::runtime_error("the host-trace library has no NCCL"); }
+inline void* nccl_comm_init(const char*, int, int) { throw std::runtime_error("the host-trace library has no NCCL"); }
+inline void nccl_comm_geometry(void*, int&, int&) { throw std::runtime_error("the host-trace library has no NCCL"); }
+inline void nccl_comm_destroy(void*) {}
+inline void exchange(const dmd::DevArrays& d, dmd::OutRec* eout, double* xb, void*, const double* gathered_host, int world,
+                     int rank, long long step, unsigned long long seed, int L, dmd::XchCounts* counts_out, double* tstar_out,
+                     double* ms, int* launches) {
+  using namespace dmd;
+  const int R = d.n_replicas, M = world * R, n_ladders = M / L;
+  std::vector<double> all(2 * (size_t)M), tnew(M);
+  if (gathered_host) {
+    std::memcpy(all.data(), gathered_host, sizeof(double) * 2 * (size_t)M);
+  } else {
+    if (world > 1) throw std::runtime_error("dmdb_exchange: more than one rank needs the gathered (E_pot, T*) array here");
+    run_op(d, 5, 0, R, 0, nullptr, eout, nullptr, nullptr);
+    for (int r = 0; r < R; r++) {
+      all[2 * r] = eout[r].ered - 0.5 * eout[r].sumvel;
+      all[2 * r + 1] = d.scal[r].setemp / 12.0;
+    }
+  }
+  XchCounts c;
+  c.attempted = c.accepted = c.changed_local = 0;
+  c.ladders = n_ladders;
+  for (int g = 0; g < M; g++) tnew[g] = all[2 * g + 1];
+  for (int l = 0; l < n_ladders; l++) xch_decide_ladder(all.data(), tnew.data(), l, L, world, R, step, seed, c.attempted, c.accepted);
+  double* tsel = xb;
+  for (int r = 0; r < R; r++) {
+    const int g = rank * R + r;
+    const bool ch = tnew[g] != all[2 * g + 1];
+    tsel[r] = ch ? tnew[g] : 0.0;
+    tstar_out[r] = tnew[g];
+    c.changed_local += ch ? 1 : 0;
+  }
+  run_op(d, 7, 0, R, 0, (int32_t*)tsel, nullptr, nullptr, nullptr);
+  *counts_out = c;
   if (ms) *ms = 0;
   if (launches) *launches = 0;
 }

@@ -125,3 +125,46 @@ def test_command_line_mirrors_dmd_stdin(monkeypatch, capsys, tab):
     assert cli.main(["--root", "/nowhere", "--nve"]) == 0
     assert seen["tstar"] == 0.2 and seen["ncoll"] == 1000000000 and seen["n"] == 1344 and seen["canon"] is False
     assert "noptotal 1344" in capsys.readouterr().out
+
+
+def _seed_results(root, golden=GOLDEN):
+    res = root / "results"
+    res.mkdir()
+    shutil.copy(os.path.join(golden, "systemA_run0000.config"), res / "run0000.config")
+    shutil.copy(os.path.join(golden, "systemA_run0000.lastvel"), res / "run0000.lastvel")
+    (res / "run0000.energy").write_text("")
+    (res / "run0000.bptnr").write_bytes(b"")
+    return res
+
+
+def check_anneal_resident_equals_chained(tmp_path, tab, system_a, lib_path, schedule):
+    """qfile/script.sh:11-18 as ONE handle with restarts on resident state (dmdb_set_temperature) against one process per
+    temperature chained through the restart files: every results file byte-identical"""
+    topo, sv, boxl = system_a
+    a, b = tmp_path / "resident", tmp_path / "chained"
+    a.mkdir()
+    b.mkdir()
+    ra, rb = _seed_results(a), _seed_results(b)
+    sa = driver.anneal(str(a), topo, tab, schedule, resident=True, boxl=boxl, lib_path=lib_path)
+    sb = driver.anneal(str(b), topo, tab, schedule, resident=False, boxl=boxl, lib_path=lib_path)
+    assert [s["run"] for s in sa] == [s["run"] for s in sb] == list(range(1, len(schedule) + 1))
+    names = sorted(os.listdir(ra))
+    assert names == sorted(os.listdir(rb)) and len(names) >= 4 + 6 * len(schedule)
+    for n in names:
+        assert (ra / n).read_bytes() == (rb / n).read_bytes(), n
+    return sa
+
+
+def test_anneal_on_resident_state_equals_chained_runs(tmp_path, tab, system_a, hosttrace_lib):
+    check_anneal_resident_equals_chained(tmp_path, tab, system_a, hosttrace_lib, [(0.5, 6000), (0.45, 5000), (0.40, 5000)])
+
+
+def test_truncated_record_keeps_the_complete_ones(tmp_path):
+    """a run killed inside config() leaves a cut record: the reader keeps what is complete (read(7,end=120))"""
+    src = os.path.join(GOLDEN, "systemA_run0000.config")
+    data = open(src, "rb").read()
+    p = tmp_path / "cut.config"
+    p.write_bytes(data + data[: len(data) // 2])
+    coll, t, xyz = fileio.read_config(str(p))
+    c0, t0, x0 = fileio.read_config(src)
+    assert coll == c0 and np.array_equal(xyz, x0)

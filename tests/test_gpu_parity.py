@@ -171,6 +171,9 @@ def test_list_rebuild_service_does_not_change_results(tab, system_a, system_b, w
     dev.set_service_ctas(3)
     compare_engines(ora, dev, replica=0, n_events=n_events)
     assert dev.stats(0).updates + dev.stats(0).forced_updates >= 10  # the lists were rebuilt by the service
+    for down in (False, True):  # ... and the lists of the last rebuild are the oracle's (sets; entry order is free)
+        a, b = ora.nbors(down), dev.nbors(0, down)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), "neighbour lists after service rebuilds (down=%s)" % down
     ref = DMD(p, topo, tab)
     ref.set_state(sv)
     ref.set_service_ctas(0)
@@ -200,13 +203,15 @@ def test_config3_temperature_ladder_with_exchange(tab, system_b):
     swaps = 0
     for step in range(8):
         dev.run(30000)
-        before = dev.potential_energies()[1].copy()
-        new_t, changed = rx.exchange_step(dev, step, seed=99, ladder_size=L)
-        swaps += changed
+        epot, before = dev.potential_energies()
+        st = dev.exchange(step, seed=99, ladder_size=L)  # dmdb_exchange: decision + temperature change on the device
+        new_t = dev.potential_energies()[1]
+        assert np.array_equal(new_t, rx.decide_swaps(epot, before, step, seed=99, ladder_size=L))  # numpy restatement
+        assert (st.ladders, st.attempted) == (2, 2 * 5) and st.changed_local == 2 * st.accepted
+        swaps += st.changed_local
         for lad in range(2):
             assert sorted(new_t[lad * L:(lad + 1) * L]) == sorted(rx.LADDER)
-        assert np.array_equal(dev.potential_energies()[1], new_t)
-        assert changed == int((new_t != before).sum())
+        assert st.changed_local == int((new_t != before).sum())
     assert swaps > 0
     dev.run(60000)
     _, tnow = dev.potential_energies()
