@@ -211,6 +211,13 @@ int dmdb_potential_energies(dmdb_handle* h, double* epot /* n_replicas */, doubl
 int dmdb_apply_temperatures(dmdb_handle* h, const double* tstar_new /* n_replicas */);
 
 
+/* beta-sheet observables of every replica, computed on the device from resident state (no trajectory download): the
+ * definitions of the reference's post-processing program results/r/fibril_list_assign.f:51-60,89,228 (one peptide
+ * species).  out: n_replicas x 8 int32 -- [0] inter-chain backbone H-bonds, [1] sheet-partner pairs (hb_contact >=
+ * chnln/2 + 1), [2] sheets (connected components of >= 2 peptides), [3] peptides in the largest sheet, [4] peptides in
+ * sheets, [5] intra-chain H-bonds, [6..7] reserved. */
+int dmdb_sheet_observables(dmdb_handle* h, int32_t* out);
+
 /* Engine 1 tuning (no reference counterpart).  The event-loop kernel gives a few of its CTAs the role of a LIST-REBUILD
  * SERVICE: they run nbor() + events() (nbor.f:33-137, events.f:23-107) for the warps of all other CTAs, so that the
  * SMs running the event loop keep only the hot loop in their 32 KB instruction caches.

@@ -13,6 +13,7 @@ from parallel_dmd_for_biomolecules_b200.tables import (EVENT_DTYPE, Energy, Even
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_LIB_FAST = None
 
 
 def build(force: bool = False) -> str:
@@ -35,13 +36,23 @@ def lib():
     return _LIB
 
 
+def lib_fast():
+    """the -O3 / AVX2 / FMA build of the same source: bench.py's CPU baseline only, never a checker"""
+    global _LIB_FAST
+    if _LIB_FAST is None:
+        build()
+        _LIB_FAST = C.CDLL(os.path.join(_HERE, "_build", "liboracle_fast.so"))
+        _LIB_FAST.dmdo_last_error.restype = C.c_char_p
+    return _LIB_FAST
+
+
 def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
 class OracleDMD:
-    def __init__(self, params: Params, topo: Topology, tables: Tables):
-        self._l = lib()
+    def __init__(self, params: Params, topo: Topology, tables: Tables, fast: bool = False):
+        self._l = lib_fast() if fast else lib()
         self._topo = topo
         self._tc = topo.to_c()
         self._h = C.c_void_p()
@@ -143,6 +154,28 @@ class OracleDMD:
         buf = C.create_string_buffer(4096)
         over = self._l.dmdo_checkover(self._h, buf, 4096)
         return bool(over), buf.value.decode()
+
+    def check_nc_int(self) -> dict:
+        """check_nc_int.f:21-360: the reference's own audit of the H-bond / auxiliary-shoulder state (m_ss != n_ss makes
+        the Fortran exit)"""
+        out = np.zeros(6, dtype=np.int32)
+        self._l.dmdo_check_nc_int(self._h, _p(out, C.c_int32))
+        return dict(zip(("boundbad", "unboundbad", "m_ss", "n_ss", "no_ss", "pairs15"), (int(x) for x in out)))
+
+    def adopt_state(self, state: dict, nbors):
+        """overwrite the live state with one read back from another engine (DMD.state() + DMD.nbors()), without the
+        restart reconstruction, so that checkover / check_nc_int audit THAT state"""
+        off, nb = nbors
+        sv = np.ascontiguousarray(state["sv"], dtype=np.float64)
+        bp = np.ascontiguousarray(state["bptnr"], dtype=np.int32)
+        idn = np.ascontiguousarray(state["identity"], dtype=np.int32)
+        er = np.ascontiguousarray(state["extra_repuls"], dtype=np.int32)
+        off = np.ascontiguousarray(off, dtype=np.int32)
+        nb = np.ascontiguousarray(nb if len(nb) else np.zeros(1), dtype=np.int32)
+        rc = self._l.dmdo_adopt_state(self._h, _p(sv, C.c_double), C.c_double(state["tfalse"]), _p(bp, C.c_int32),
+                                      _p(idn, C.c_int32), _p(er, C.c_int32), _p(off, C.c_int32), _p(nb, C.c_int32))
+        if rc != 0:
+            raise RuntimeError(self._l.dmdo_last_error().decode())
 
     def event_log(self, first=0, n=1 << 20):
         out = np.zeros(n, dtype=EVENT_DTYPE)

@@ -1176,6 +1176,63 @@ EnergyRec Oracle::energy() const {
   return e;
 }
 
+// check_nc_int.f:21-360.  The four species branches of the Fortran (:31-50, :118-124, :205-211, :292-298) differ only in
+// the "no end bead" test, which is terminal_ok() (same expressions as main.F90:1490-1491 etc.).  Loop over the up-lists
+// (nb / na_npt, :24-29), pairs with ev_code(j,i) == 15 only.
+Oracle::NcAudit Oracle::check_nc_int() const {
+  NcAudit a;
+  for (int i = 1; i <= noptotal; i++) {
+    const int kstart = (i - 1) * maxnbs + 1, kend = kstart + na_npt[i] - 1;
+    for (int k = kstart; k <= kend; k++) {
+      const int j = nb[k];
+      if (ev(j, i) != 15) continue;
+      a.pairs15++;
+      const int ii = local_index(i), jj = local_index(j);
+      const bool inner = terminal_ok(i, ii, j, jj);
+      if (bptnr[i] == j) {  // counted as a hydrogen bond: the four auxiliary distances must be legal (:43-57)
+        double rating = 10.0;
+        if (inner) rating = identity[i] < identity[j] ? repuls_check(i, j) : repuls_check(j, i);
+        if (rating > 10.0) a.boundbad++;
+        if (inner) {
+          if (ER(i, 4) == j) a.n_ss++;
+          else a.no_ss++;  // print*, 'no ss for bond'
+        }
+      } else {  // not bonded: inside the well with good geometry should not happen (:66-105)
+        PairGeom g = geom(&sv[(size_t)i * 6], &sv[(size_t)j * 6], tfalse);
+        const double rijsq = g.rx * g.rx + g.ry * g.ry + g.rz * g.rz;
+        const double diff = rijsq - welldia_sq[identity[i]][identity[j]];
+        if (diff < 0.0) {
+          double rating = 11.0;  // an end bead is involved: "we'll let this slide"
+          if (inner) rating = identity[i] < identity[j] ? repuls_check(i, j) : repuls_check(j, i);
+          if (rating <= 10.0) a.unboundbad++;
+          if (inner) {
+            if (ER(i, 4) == j) a.n_ss++;
+            else a.no_ss++;  // print*, 'no ss for non-bond'
+          }
+        }
+      }
+      if (ER(i, 4) == j) a.m_ss++;  // :107-110
+    }
+  }
+  return a;
+}
+
+void Oracle::adopt_state(const double* sv6xN, double tfalse_, const int* bptnr_, const int* identity_, const int* er,
+                         const int* off, const int* lst) {
+  const int N = noptotal;
+  tfalse = tfalse_;
+  for (int k = 1; k <= N; k++) {
+    for (int c = 0; c < 6; c++) sv[(size_t)k * 6 + c] = sv6xN[(size_t)(k - 1) * 6 + c];
+    bptnr[k] = bptnr_[k - 1];
+    identity[k] = identity_[k - 1];
+    for (int s4 = 1; s4 <= 4; s4++) ER(k, s4) = er[(size_t)(s4 - 1) * N + (k - 1)];
+    const int cnt = off[k] - off[k - 1];
+    if (cnt > maxnbs) throw std::runtime_error("adopt_state: list longer than maxnbs");
+    na_npt[k] = cnt;
+    for (int q = 0; q < cnt; q++) nb[(size_t)(k - 1) * maxnbs + 1 + q] = lst[off[k - 1] + q];
+  }
+}
+
 // checkover.f:21-131 (returns true when an overlap / bond violation exists)
 bool Oracle::checkover(std::string* why) const {
   bool over = false;
@@ -1241,7 +1298,9 @@ void Oracle::set_state(const double* sv6xN, const int* bp) {
     for (int c = 0; c < 6; c++) sv[(size_t)k * 6 + c] = sv6xN[(size_t)(k - 1) * 6 + c];
     for (int c = 1; c <= 3; c++) S(c, k) = S(c, k) - dnint(S(c, k));  // inputinfo.f:89-91
   }
-  // a fresh program start: identity and ev_code overlay are reset
+  // a fresh program start: the random-number stream starts over (main.F90:171-174 seeds drandm with the fixed iflag at
+  // every `./dmd` run; D2: the counter of the replica's stream goes back to zero), identity and ev_code overlay are reset
+  rng_ctr = 0;
   for (int l = 1; l <= nop1; l += numbeads1)
     for (int k = 1; k <= numbeads1; k++) identity[l + k - 1] = aa[k];
   for (int l = nop1 + 1; l <= nop1 + nop2; l += numbeads2)

@@ -78,6 +78,17 @@ class Oracle {
   double check_sigma(int i, int j) const;              // check_sigma.f:12-29
   EnergyRec energy() const;                            // energy.f:25-101
   bool checkover(std::string* why = nullptr) const;    // checkover.f:21-131 (returns over)
+  // check_nc_int.f:21-360 (called at main.F90:425 and, under -Ddebugging, at every output event :1199): the audit of
+  // the H-bond <-> auxiliary-shoulder state machine.  Adds to boundbad / unboundbad like the Fortran, returns
+  // m_ss / n_ss (the reference exits when they differ) and the number of its "no ss for ..." complaints.
+  struct NcAudit {
+    int boundbad = 0, unboundbad = 0, m_ss = 0, n_ss = 0, no_ss = 0, pairs15 = 0;
+  };
+  NcAudit check_nc_int() const;
+  // test hook: overwrite the live state with one read back from another engine (no restart reconstruction), so that
+  // the same audit runs on device state.  Arrays 0-based, bead indices 1-based (0 = none), lists as dmdb_get_nbors.
+  void adopt_state(const double* sv6xN, double tfalse_, const int* bptnr_, const int* identity_, const int* extra_repuls_Nx4,
+                   const int* nb_offsets, const int* nb_list);
 
   // ---- main loop, serial semantics (main.F90:484-1258)
   void step();                      // one calendar event

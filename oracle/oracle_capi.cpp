@@ -144,6 +144,18 @@ int dmdo_checkover(void* h, char* why, int why_len) {
   return over ? 1 : 0;
 }
 
+int dmdo_check_nc_int(void* h, int32_t* out /* boundbad, unboundbad, m_ss, n_ss, no_ss, pairs15 */) {
+  Oracle* o = (Oracle*)h;
+  const Oracle::NcAudit a = o->check_nc_int();
+  out[0] = a.boundbad; out[1] = a.unboundbad; out[2] = a.m_ss; out[3] = a.n_ss; out[4] = a.no_ss; out[5] = a.pairs15;
+  return 0;
+}
+
+int dmdo_adopt_state(void* h, const double* sv, double tfalse, const int32_t* bptnr, const int32_t* identity,
+                     const int32_t* extra_repuls, const int32_t* nb_offsets, const int32_t* nb) {
+  GUARD(((Oracle*)h)->adopt_state(sv, tfalse, bptnr, identity, extra_repuls, nb_offsets, nb))
+}
+
 int dmdo_get_event_log(void* h, int64_t first, int64_t n, dmdb_event* out, int64_t* n_out) {
   Oracle* o = (Oracle*)h;
   int64_t m = 0;

@@ -645,6 +645,29 @@ int dmdb_energy_of(dmdb_handle* h, int replica, dmdb_energy* e) {
   return DMDB_OK;
 }
 
+int dmdb_sheet_observables(dmdb_handle* h, int32_t* out) {
+  int rc = all_loaded(h);
+  if (rc) return rc;
+  if (!out) return fail(h, DMDB_ERR_ARG, "null argument");
+  const dmd::SysConst& s = h->model.sys;
+  if (s.n_species == 2 && s.nch[1] > 0 && (s.numbeads[1] != s.numbeads[0] || s.chnln[1] != s.chnln[0]))
+    return fail(h, DMDB_ERR_ARG, "sheet observables: fibril_list_assign.f handles one peptide species (equal chains)");
+  if (s.N / s.numbeads[0] > be::sheet_max_chains()) return fail(h, DMDB_ERR_CAPACITY, "sheet observables: too many chains");
+  const size_t R = (size_t)h->d.n_replicas;
+  DMDB_TRY(h, {
+    int32_t* dev = (int32_t*)be::alloc(R * 8 * sizeof(int32_t));
+    try {
+      be::run_sheets(h->d, dev);
+      be::d2h(out, dev, R * 8 * sizeof(int32_t));
+    } catch (...) {
+      be::release(dev);
+      throw;
+    }
+    be::release(dev);
+  })
+  return DMDB_OK;
+}
+
 int dmdb_potential_energies(dmdb_handle* h, double* epot, double* tstar) {
   int rc = all_loaded(h);
   if (rc) return rc;

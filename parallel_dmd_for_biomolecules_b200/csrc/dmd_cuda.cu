@@ -131,6 +131,9 @@ struct alignas(16) EvlSmem {
 #define DMD_SVC_GROUPS 2  // a service CTA works as this many independent groups of warps, one replica each: with one
                           // bead per thread a 1344-bead replica leaves a third of 896 threads idle in its second round
 #endif
+#ifndef DMD_CHAINWISE_MAX_NEAR
+#define DMD_CHAINWISE_MAX_NEAR 6  // chain-wise list rebuild while a chain has at most this many chains within reach (mean)
+#endif
 __device__ __forceinline__ void svc_group_sync(int grp, int gsz) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(gsz) : "memory"); }
 
 __device__ __noinline__ void svc_serve_in_kernel(DevArrays d, int r0, int nrep, unsigned char* scratch, size_t scratch_bytes) {
@@ -182,24 +185,48 @@ __device__ __noinline__ void svc_serve_in_kernel(DevArrays d, int r0, int nrep, 
     // spheres, near-chain masks -- lives in the group's share of the CTA's static shared memory
     const int nch = d.n_chains;
     const size_t cw_bytes = (size_t)d.n_beads * 4 + (size_t)nch * (sizeof(evl::ChainBound) + 8) + 32;
+    bool cell_walk = true;
+    // Small systems (SysConst.chainwise): two candidate searches that avoid the linked-list walk, chosen per rebuild by
+    // how many chains come within reach of one another (measured on B200, 48-peptide boxes, per rebuild and group of 14
+    // warps: dilute box  chain-wise 112 us, sorted grid 257 us, cell walk ~190 us; aggregated box  sorted grid 842 us,
+    // chain-wise ~1700 us, cell walk ~1700 us).  Scratch = the group's share of the CTA's static shared memory.
+    const size_t sg_end_words = ((size_t)d.ncc3 + 2 + 1) & ~(size_t)1, sg_sorted_words = ((size_t)d.n_beads + 1) & ~(size_t)1;
+    const size_t sg_bytes = (sg_end_words + sg_sorted_words) * 2 + (size_t)nt * 4;
     if (d.chainwise && cw_bytes <= scratch_bytes) {
       evl::ChainBound* const cbound = reinterpret_cast<evl::ChainBound*>(scratch);
       unsigned* const near = reinterpret_cast<unsigned*>(cbound + nch);
       uint32_t* const cpk = near + 2 * nch;
       for (int k = tid; k < 2 * nch; k += nt) near[k] = 0u;
+      if (tid == 0) s_pick[grp] = 0;  // (free between two picks) number of near chain pairs
       evl::chainwise_cells(q, cpk, tid, nt);
       evl::chainwise_bounds(q, cbound, nch, tid >> 5, nt >> 5);
       svc_group_sync(grp, gsz);
       evl::chainwise_near(q, cbound, near, nch, tid, nt);
       svc_group_sync(grp, gsz);
-      const long long t1 = clock64();
-      evl::chainwise_lists(q, cpk, near, tid, nt);
+      for (int k = tid; k < 2 * nch; k += nt) atomicAdd(&s_pick[grp], __popc(near[k]));
       svc_group_sync(grp, gsz);
-      if (tid == 0) {
+      const bool sparse = s_pick[grp] <= DMD_CHAINWISE_MAX_NEAR * nch;
+      const long long t1 = clock64();
+      if (sparse) {  // dilute: a chain has a few chains within reach
+        evl::chainwise_lists(q, cpk, near, tid, nt);
+        cell_walk = false;
+      } else if (d.n_beads < 65536 && sg_bytes <= scratch_bytes) {  // aggregated: every chain is near most others
+        svc_group_sync(grp, gsz);  // (the scratch changes hands)
+        evl::SortedGrid sg;
+        sg.end = reinterpret_cast<uint16_t*>(scratch);
+        sg.sorted = sg.end + sg_end_words;
+        sg.tot = reinterpret_cast<unsigned*>(sg.sorted + sg_sorted_words);
+        evl::sorted_grid_build(q, sg, tid, nt, [&]() { svc_group_sync(grp, gsz); });
+        evl::sorted_grid_lists(q, sg, tid >> 5, nt >> 5);
+        cell_walk = false;
+      }
+      svc_group_sync(grp, gsz);
+      if (tid == 0 && !cell_walk) {
         atomicAdd(&d.svc_ctl[5], (unsigned long long)(t1 - t0));
         atomicAdd(&d.svc_ctl[6], (unsigned long long)(clock64() - t1));
       }
-    } else {
+    }
+    if (cell_walk) {
       if (grid_fits) {
         for (int k = tid; k < d.ncc3; k += nt) s_heads[k] = -1;
         q.cellhead = s_heads;
@@ -551,6 +578,20 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_energy_kernel(DevArray
   if (Warp::lane() == 0) eout[rid] = o;
 }
 
+// beta-sheet observables (fibril_list_assign.f definitions) of every replica, one warp each, from resident state
+constexpr int SHEET_WARPS = 4;
+constexpr int SHEET_MAX_CHAINS = 96;
+__global__ void __launch_bounds__(SHEET_WARPS * 32) dmd_sheet_kernel(DevArrays d, int nrep, int32_t* out) {
+  __shared__ uint8_t s_hb[SHEET_WARPS][SHEET_MAX_CHAINS * SHEET_MAX_CHAINS];
+  __shared__ int32_t s_lab[SHEET_WARPS][SHEET_MAX_CHAINS];
+  const int w = threadIdx.x >> 5;
+  const int rid = blockIdx.x * SHEET_WARPS + w;
+  if (rid >= nrep) return;
+  Rep r;
+  rep_bind(r, d, staged_global(d), nullptr, rid);
+  sheet_observables(r, out + 8 * (size_t)rid, s_hb[w], s_lab[w]);
+}
+
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dmd_retemp_kernel(DevArrays d, int r0, int nrep, const double* tstar_new) {
   __shared__ SmemConsts sconst;
   const Staged tab = stage_consts(d, &sconst);
@@ -889,6 +930,13 @@ inline void run_init(const dmd::DevArrays& d, int r0, int nrep, const double* sv
   dmd_fixup_kernel<<<(nrep + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, 0, g_stream>>>(d, r0, nrep);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(g_stream));
+}
+inline int sheet_max_chains() { return dmd::SHEET_MAX_CHAINS; }
+inline void run_sheets(const dmd::DevArrays& d, int32_t* out_dev) {
+  using namespace dmd;
+  bind();
+  dmd_sheet_kernel<<<(d.n_replicas + SHEET_WARPS - 1) / SHEET_WARPS, SHEET_WARPS * 32, 0, g_stream>>>(d, d.n_replicas, out_dev);
+  CUDA_OK(cudaGetLastError());
 }
 inline void run_pack(const dmd::DevArrays& d, double* sv, int32_t* bp) {
   bind();

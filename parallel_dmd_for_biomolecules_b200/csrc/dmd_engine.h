@@ -1364,6 +1364,7 @@ DMD_DEV void chainwise_lists(Rep& r, const uint32_t* cpk, const unsigned* near, 
       const int own_lo = kk - meta_local(mk);
       const uint8_t* const sct_row = r.c.sctab + s.sct_off[sp] + (size_t)meta_local(mk) * nb;
       const int nbmax = s.numbeads[0] > s.numbeads[1] ? s.numbeads[0] : s.numbeads[1];
+#pragma unroll 4
       for (int lj = 0; lj < nbmax; lj++) {
         const int j = own_lo + lj;
         if (!live || lj >= nb || j == k) continue;
@@ -1385,7 +1386,8 @@ DMD_DEV void chainwise_lists(Rep& r, const uint32_t* cpk, const unsigned* near, 
         const int c = half * 32 + bit;
         const bool mine = (mine_mask >> bit) & 1u;
         const int f = (chain_first)(s, c), nb = (chain_len)(s, c);
-        for (int lj = 0; lj < nb; lj++) {
+#pragma unroll 4
+        for (int lj = 0; lj < nb; lj++) {  // (unrolled: the cell words of four candidates are in flight together)
           const int j = f + lj;
           if (!mine) continue;
           const uint32_t pj = cpk[j];
@@ -1406,6 +1408,196 @@ DMD_DEV void chainwise_lists(Rep& r, const uint32_t* cpk, const unsigned* near, 
     }
   }
   if (overflow) {  // reported through the stored scalars (the service CTA has no replica view of its own)
+    if (atomicCAS(&r.sc->error, 0, DMD_E_NBR_CAP) == 0) r.sc->error_info = overflow;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Sorted-grid list rebuild (service CTAs; any density).  The beads are counting-sorted by COARSE cell (2 x 2 x 2 fine
+// cells) into a 16-bit index array in shared memory, with 16-bit cell end offsets beside it: a bead's candidates are
+// then short contiguous runs of that array -- no linked lists through global memory, no per-candidate chain of
+// dependent loads -- filtered by the exact fine-cell test and classified from the same-chain table or the closed
+// inter-chain rule.  Same neighbour sets as nbor_build() / nbor.f:33-137; entries ordered by (coarse cell in scan
+// order, bead index): deterministic.  Needs N < 65536 and (ncc^3 + 1 + N) 16-bit words of scratch.
+// ---------------------------------------------------------------------------------------------------------
+struct SortedGrid {
+  uint16_t* end;     // ncc3 + 1 entries: end[c] = one past the last slot of coarse cell c (start = end[c - 1], 0 for c = 0)
+  uint16_t* sorted;  // N entries: bead indices grouped by coarse cell, ascending inside a cell
+  unsigned* tot;     // one word per thread of the group (prefix sum over the cells)
+};
+DMD_DEV unsigned sg_add16(uint16_t* a, int c, unsigned v) {  // 16-bit atomic add in shared memory; returns the old value
+  const unsigned old = atomicAdd(reinterpret_cast<unsigned*>(a) + (c >> 1), v << (16 * (c & 1)));
+  return (old >> (16 * (c & 1))) & 0xffffu;
+}
+// steps 1-4, all threads of the group (gsync = the group's barrier)
+template <class Sync>
+DMD_DEV void sorted_grid_build(Rep& r, SortedGrid g, int tid, int nt, Sync gsync) {
+  const SysConst& s = *r.c.sys;
+  const int ncr = s.ncr, nc = s.num_cell, nw = s.n_wrap, ncc = coarse_dim(ncr), ncc3 = ncc * ncc * ncc;
+  for (int c = tid; c < (ncc3 + 2) / 2; c += nt) reinterpret_cast<unsigned*>(g.end)[c] = 0u;
+  gsync();
+  for (int k = tid; k < r.N; k += nt) {  // fine coordinates (cell_add.f:22), reference cell id, coarse cell population
+    int cx, cy, cz;
+    (cell_coords)(s, r.rec[k], cx, cy, cz);
+    r.cellof[k] = 1 + (cx + nw) + (cy + nw) * nc + (cz + nw) * nc * nc;  // cell_add.f:25
+    if (cx < 0 || cy < 0 || cz < 0 || cx >= ncr || cy >= ncr || cz >= ncr) {
+      r.cpk[k] = CPK_OUT;  // the reference files the bead in a ghost cell that is never looked up
+      continue;
+    }
+    r.cpk[k] = cpk_pack(cx, cy, cz);
+    sg_add16(g.end, (cx >> 1) + ((cy >> 1) + (cz >> 1) * ncc) * ncc, 1u);
+  }
+  gsync();
+  // exclusive prefix sum in place: a contiguous slice per thread, the slice totals scanned by thread 0, then every
+  // slice adds its base
+  const int per = (ncc3 + nt - 1) / nt;
+  const int c0 = tid * per, c1 = c0 + per < ncc3 ? c0 + per : ncc3;
+  unsigned sum = 0;
+  for (int c = c0; c < c1; c++) sum += g.end[c];
+  unsigned* const tot = g.tot;
+  tot[tid] = sum;
+  gsync();
+  if (tid == 0) {
+    unsigned run = 0;
+    for (int t = 0; t < nt; t++) {
+      const unsigned v = tot[t];
+      tot[t] = run;
+      run += v;
+    }
+  }
+  gsync();
+  unsigned run = tot[tid];
+  gsync();
+  for (int c = c0; c < c1; c++) {
+    const unsigned v = g.end[c];
+    g.end[c] = (uint16_t)run;  // start of the cell; the scatter below advances it to the cell's end
+    run += v;
+  }
+  gsync();
+  for (int k = tid; k < r.N; k += nt) {
+    const uint32_t pk = r.cpk[k];
+    if (pk == CPK_OUT) continue;
+    const int c = (int)((pk & 1023u) >> 1) + ((int)(((pk >> 10) & 1023u) >> 1) + (int)((pk >> 20) >> 1) * ncc) * ncc;
+    g.sorted[sg_add16(g.end, c, 1u)] = (uint16_t)k;
+  }
+  gsync();
+  for (int c = tid; c < ncc3; c += nt) {  // ascending bead index inside every cell: the scatter order is arbitrary
+    const int a = c ? g.end[c - 1] : 0, b = g.end[c];
+    for (int i = a + 1; i < b; i++) {
+      const uint16_t v = g.sorted[i];
+      int j = i - 1;
+      while (j >= a && g.sorted[j] > v) {
+        g.sorted[j + 1] = g.sorted[j];
+        j--;
+      }
+      g.sorted[j + 1] = v;
+    }
+  }
+  gsync();
+}
+// step 5 (one HARDWARE warp per bead, lanes over its candidates): both lists of every bead.  The coarse cells of the
+// bead's stencil are taken by the lanes (one cell each), their populations prefix-summed over the warp, and the
+// candidates -- the concatenation of the cells' runs of sorted[] -- tested 32 at a time: cell word, fine-cell filter,
+// class, distance, all lanes in flight together; the survivors are appended in candidate order (ballot + popc).
+DMD_DEV void sorted_grid_lists(Rep& r, SortedGrid g, int warp, int nwarps) {
+  const SysConst& s = *r.c.sys;
+  const int cap = r.cap, ncr = s.ncr, ncc = coarse_dim(ncr);
+  const int lane = threadIdx.x & 31;
+  const unsigned FULL = 0xffffffffu;
+  int overflow = 0;
+  for (int k = warp; k < r.N; k += nwarps) {  // warp-uniform
+    const uint32_t pk = r.cpk[k];
+    int nu = 0, nd = 0;
+    if (pk != CPK_OUT) {
+      const BeadRec* pkr = &r.rec[k];
+      const double xk = pkr->x, yk = pkr->y, zk = pkr->z;
+      const uint32_t mk = r.c.meta[k];
+      const int ck = r.c.chain[k];
+      const int sp = meta_sp(mk), nb = s.numbeads[sp];
+      const int own_lo = k - meta_local(mk);
+      const uint8_t* const sct_row = r.c.sctab + s.sct_off[sp] + (size_t)meta_local(mk) * nb;
+      int xs[4], ys[4], zs[4];
+      const int nx = coarse_span((int)(pk & 1023u), ncr, xs), ny = coarse_span((int)((pk >> 10) & 1023u), ncr, ys),
+                nz = coarse_span((int)(pk >> 20), ncr, zs);
+      const int ncell = nx * ny * nz;  // <= 64
+      for (int q0 = 0; q0 < ncell; q0 += 32) {
+        // ---- one coarse cell per lane: its run [a, a + cnt) of sorted[]
+        const int q = q0 + lane;
+        int a = 0, cnt = 0;
+        if (q < ncell) {
+          const int iz = q / (nx * ny), rem = q - iz * nx * ny, iy = rem / nx, ix = rem - iy * nx;
+          const int c = xs[ix] + (ys[iy] + zs[iz] * ncc) * ncc;
+          a = c ? g.end[c - 1] : 0;
+          cnt = (int)g.end[c] - a;
+        }
+        int incl = cnt;  // inclusive prefix sum of the populations over the lanes
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int o = __shfl_up_sync(FULL, incl, d);
+          if (lane >= d) incl += o;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        const int excl = incl - cnt;
+        for (int t0 = 0; t0 < total; t0 += 32) {
+          const int idx = t0 + lane;
+          // the lane whose run holds candidate idx: the first lane with incl > idx (binary search over the warp)
+          int lo = 0;
+#pragma unroll
+          for (int step = 16; step >= 1; step >>= 1) {
+            const int probe = __shfl_sync(FULL, incl, lo + step - 1);
+            if (probe <= idx) lo += step;
+          }
+          const int src = lo & 31;
+          const int a_src = __shfl_sync(FULL, a, src), excl_src = __shfl_sync(FULL, excl, src);
+          bool in = false;
+          int j = -1, sc = 1;
+          if (idx < total) {
+            j = g.sorted[a_src + (idx - excl_src)];
+            if (j != k && in_fine_stencil(pk, r.cpk[j], ncr)) {
+              if (j >= own_lo && j < own_lo + nb) {
+                sc = (int)sct_row[j - own_lo];
+                in = code_is_bonded_class(sc);  // nbor.f:60
+              } else {
+                sc = static_code(s, mk, ck, k, r.c.meta[j], ck + 1, j);  // another chain: 1, 15 or 16
+              }
+              if (!in) {  // nbor.f:97-105 (the cut-off of class 1 also holds for its 40 / 50 overlay: SysConst.chainwise)
+                const BeadRec* pj = &r.rec[j];
+                double rx = xk - pj->x, ry = yk - pj->y, rz = zk - pj->z;
+                rx = rx - dmd_round(rx);
+                ry = ry - dmd_round(ry);
+                rz = rz - dmd_round(rz);
+                in = rx * rx + ry * ry + rz * rz <= s.rlsq[sc];
+              }
+            }
+          }
+          const unsigned mu = __ballot_sync(FULL, in && j > k), md = __ballot_sync(FULL, in && j < k);
+          const unsigned below = (1u << lane) - 1u;
+          if (in) {
+            const uint32_t e = ((uint32_t)sc << NB_SHIFT) | (uint32_t)j;
+            if (j > k) {
+              const int pos = nu + __popc(mu & below);
+              if (pos < cap) r.up[(size_t)k * cap + pos] = e;
+            } else {
+              const int pos = nd + __popc(md & below);
+              if (pos < cap) r.dn[(size_t)k * cap + pos] = e;
+            }
+          }
+          nu += __popc(mu);
+          nd += __popc(md);
+        }
+      }
+    }
+    if (nu > cap || nd > cap) {
+      overflow = nu > nd ? nu : nd;
+      nu = nu > cap ? cap : nu;
+      nd = nd > cap ? cap : nd;
+    }
+    if (lane == 0) {
+      r.nup[k] = (uint16_t)nu;
+      r.ndn[k] = (uint16_t)nd;
+    }
+  }
+  if (overflow && lane == 0) {
     if (atomicCAS(&r.sc->error, 0, DMD_E_NBR_CAP) == 0) r.sc->error_info = overflow;
   }
 }
@@ -1762,6 +1954,90 @@ DMD_DEV void retemp(Rep& r, double tstar_new) {
   Warp::sync();
   nbor(r);
   predict_all(r);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// beta-sheet observables of one replica from its resident state, the definitions of the reference's
+// post-processing program results/r/fibril_list_assign.f (one peptide species, as there):
+//   hb_contact(a,b)  inter-chain backbone H-bonds of peptides a, b: bptnr over the N and C beads of each chain except
+//                    the first N and the last C (:51-60)
+//   sheet partners   hb_contact(a,b) >= chnln/2 + 1 (:89); a sheet = a connected component of that relation (:228)
+// out[0] inter-chain H-bonds, [1] sheet-partner pairs, [2] sheets (>= 2 peptides), [3] largest sheet, [4] peptides in
+// sheets, [5] intra-chain H-bonds, [6..7] 0.  hbm: nc x nc bytes of scratch, lab: nc ints (shared memory on the device).
+// ---------------------------------------------------------------------------------------------------------
+DMD_DEV void sheet_observables(const Rep& r, int32_t* out, uint8_t* hbm, int32_t* lab) {
+  const SysConst& s = *r.c.sys;
+  const int L = s.chnln[0], nbd = s.numbeads[0];
+  const int nc = r.N / nbd;
+  Warp::sync();
+  for (int k = Warp::lane(); k < nc * nc; k += DMD_W) hbm[k] = 0;
+  for (int k = Warp::lane(); k < nc; k += DMD_W) lab[k] = k;
+  Warp::sync();
+  int hb_inter = 0, hb_intra = 0;
+  for (int aa = Warp::lane(); aa < r.N; aa += DMD_W) {
+    const int bb = r.rec[aa].bptnr;
+    if (bb <= aa) continue;  // every bond once (bptnr is symmetric)
+    const int ca = aa / nbd, cb = bb / nbd;
+    if (ca == cb) {
+      hb_intra++;
+      continue;
+    }
+    hb_inter++;
+    const int la = aa - ca * nbd, lb = bb - cb * nbd;  // 0-based index in the chain; inner = 1-based L+2 .. 3L-1
+    if (la >= L + 1 && la <= 3 * L - 2 && lb >= L + 1 && lb <= 3 * L - 2) {
+#if DMD_W > 1
+      // byte counters in shared memory: one 32-bit atomic add on the containing word
+      const int idx = ca * nc + cb;
+      atomicAdd(reinterpret_cast<unsigned*>(hbm) + (idx >> 2), 1u << (8 * (idx & 3)));
+#else
+      hbm[ca * nc + cb]++;
+#endif
+    }
+  }
+  hb_inter = warp_sum(hb_inter);
+  hb_intra = warp_sum(hb_intra);
+  Warp::sync();
+  const int need = L / 2 + 1;
+  int dimers = 0;
+  for (int k = Warp::lane(); k < nc * nc; k += DMD_W) {
+    const int a = k / nc, b = k - a * nc;
+    if (a < b && hbm[a * nc + b] + hbm[b * nc + a] >= need) dimers++;
+  }
+  dimers = warp_sum(dimers);
+  // connected components by label propagation (labels only decrease; at most nc sweeps)
+  for (int sweep = 0; sweep < nc; sweep++) {
+    bool changed = false;
+    for (int a = Warp::lane(); a < nc; a += DMD_W) {
+      int m = lab[a];
+      for (int b = 0; b < nc; b++)
+        if (b != a && hbm[a * nc + b] + hbm[b * nc + a] >= need && lab[b] < m) m = lab[b];
+      if (m < lab[a]) {
+        lab[a] = m;
+        changed = true;
+      }
+    }
+    Warp::sync();
+    if (!Warp::any(changed)) break;
+  }
+  int sheets = 0, largest = 0, in_sheets = 0;
+  for (int a = Warp::lane(); a < nc; a += DMD_W) {
+    if (lab[a] != a) continue;  // a is the root of its component
+    int size = 0;
+    for (int b = 0; b < nc; b++) size += lab[b] == a ? 1 : 0;
+    if (size >= 2) {
+      sheets++;
+      in_sheets += size;
+      largest = size > largest ? size : largest;
+    }
+  }
+  sheets = warp_sum(sheets);
+  in_sheets = warp_sum(in_sheets);
+  largest = warp_max_u(largest);
+  if (Warp::lane() == 0) {
+    out[0] = hb_inter; out[1] = dimers; out[2] = sheets; out[3] = largest; out[4] = in_sheets; out[5] = hb_intra;
+    out[6] = out[7] = 0;
+  }
+  Warp::sync();
 }
 
 // main.F90:1288-1295 (then the state must be re-initialised by the host before running on)

@@ -29,7 +29,7 @@ SYMBOLS = [
     "dmdb_get_event_log", "dmdb_get_replica_stats", "dmdb_potential_energies", "dmdb_set_state_all",
     "dmdb_get_state_all", "dmdb_apply_temperatures", "dmdb_get_batch_stats", "dmdb_run_until_output",
     "dmdb_device_fill", "dmdb_set_service_ctas", "dmdb_nccl_unique_id", "dmdb_comm_init", "dmdb_exchange",
-    "dmdb_exchange_gathered",
+    "dmdb_exchange_gathered", "dmdb_sheet_observables",
 ]
 
 
@@ -206,6 +206,13 @@ class DMD:
         e = Energy()
         self._chk(self._l.dmdb_energy_of(self._h, replica, C.byref(e)))
         return e
+
+    def sheet_observables(self) -> np.ndarray:
+        """(n_replicas, 8) int32 from the device: inter-chain H-bonds, sheet-partner pairs, sheets, largest sheet, peptides
+        in sheets, intra-chain H-bonds (fibril_list_assign.f definitions; observables.py is the numpy restatement)"""
+        out = np.zeros((self.n_replicas, 8), dtype=np.int32)
+        self._chk(self._l.dmdb_sheet_observables(self._h, _p(out, C.c_int32)))
+        return out
 
     def potential_energies(self):
         ep = np.zeros(self.n_replicas)

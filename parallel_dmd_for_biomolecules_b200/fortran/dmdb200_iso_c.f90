@@ -23,6 +23,8 @@ module dmdb200
   public :: dmdb_energy_of, dmdb_get_event_log, dmdb_get_replica_stats
   public :: dmdb_potential_energies, dmdb_apply_temperatures, dmdb_get_batch_stats
   public :: dmdb_device_fill, dmdb_set_service_ctas
+  public :: dmdb_exchange_stats, dmdb_nccl_unique_id, dmdb_comm_init, dmdb_exchange, dmdb_exchange_gathered
+  public :: dmdb_sheet_observables
   public :: dmdb_error_message
   public :: DMDB_OK, DMDB_ERR_ARG, DMDB_ERR_NO_DEVICE, DMDB_ERR_CUDA, DMDB_ERR_STATE, DMDB_ERR_CAPACITY, &
             DMDB_ERR_PHYSICS, DMDB_MAX_SPECIES
@@ -69,6 +71,12 @@ module dmdb200
     integer(c_int64_t) :: events, pair_events
     integer(c_int64_t) :: nevents(32)
     integer(c_int64_t) :: ghosts, updates, forced_updates, pair_predictions, nbr_visits
+    real(c_double) :: device_ms
+    integer(c_int32_t) :: kernel_launches, reserved
+  end type
+
+  type, bind(C) :: dmdb_exchange_stats   ! one replica-exchange step (dmdb_exchange)
+    integer(c_int32_t) :: ladders, attempted, accepted, changed_local
     real(c_double) :: device_ms
     integer(c_int32_t) :: kernel_launches, reserved
   end type
@@ -252,6 +260,50 @@ module dmdb200
       import :: c_ptr, c_int, c_double
       type(c_ptr), value :: handle
       real(c_double), intent(in) :: tstar_new(*)
+      integer(c_int) :: rc
+    end function
+    ! replica exchange on the device (new functionality; the reference runs temp_0xx one after the other,
+    ! qfile/script.sh:11-18).  comm: an ncclComm_t the host created (c_loc / c_ptr), or c_null_ptr for the
+    ! communicator of dmdb_comm_init.
+    function dmdb_nccl_unique_id(id) bind(C, name="dmdb_nccl_unique_id") result(rc)
+      import :: c_int, c_char
+      character(kind=c_char), intent(out) :: id(128)
+      integer(c_int) :: rc
+    end function
+    function dmdb_comm_init(handle, id, world, rank) bind(C, name="dmdb_comm_init") result(rc)
+      import :: c_ptr, c_int, c_char
+      type(c_ptr), value :: handle
+      character(kind=c_char), intent(in) :: id(128)
+      integer(c_int), value :: world, rank
+      integer(c_int) :: rc
+    end function
+    function dmdb_exchange(handle, comm, step, seed, ladder_size, stats) bind(C, name="dmdb_exchange") result(rc)
+      import :: c_ptr, c_int, c_int32_t, c_int64_t, dmdb_exchange_stats
+      type(c_ptr), value :: handle, comm
+      integer(c_int64_t), value :: step, seed
+      integer(c_int32_t), value :: ladder_size
+      type(dmdb_exchange_stats), intent(out) :: stats
+      integer(c_int) :: rc
+    end function
+    ! the same decision + temperature change when the host gathers (E_pot, T*) itself (MPI_Allgather):
+    ! gathered(2, n_replicas, world), rank-major
+    function dmdb_exchange_gathered(handle, gathered, world, rank, step, seed, ladder_size, stats) &
+        bind(C, name="dmdb_exchange_gathered") result(rc)
+      import :: c_ptr, c_int, c_int32_t, c_int64_t, c_double, dmdb_exchange_stats
+      type(c_ptr), value :: handle
+      real(c_double), intent(in) :: gathered(*)
+      integer(c_int), value :: world, rank
+      integer(c_int64_t), value :: step, seed
+      integer(c_int32_t), value :: ladder_size
+      type(dmdb_exchange_stats), intent(out) :: stats
+      integer(c_int) :: rc
+    end function
+    ! beta-sheet observables of every replica from resident state (results/r/fibril_list_assign.f definitions):
+    ! out(8, n_replicas)
+    function dmdb_sheet_observables(handle, out) bind(C, name="dmdb_sheet_observables") result(rc)
+      import :: c_ptr, c_int, c_int32_t
+      type(c_ptr), value :: handle
+      integer(c_int32_t), intent(out) :: out(*)
       integer(c_int) :: rc
     end function
     function dmdb_device_fill(device, n_replicas, n_service_ctas) bind(C, name="dmdb_device_fill") result(rc)

@@ -48,7 +48,9 @@ def hosttrace_lib():
 
 def compare_engines(ora, dev, replica=0, n_events=0, time_rtol=1e-12):
     """The parity surface of BASELINE.json's north_star: bit-exact cells / neighbour sets / next-event partner and
-    type, event times within 1e-12 relative, identical committed-event sequence."""
+    type, event times within 1e-12 relative, identical committed-event sequence.  The engine is held to more than
+    the stated tolerance: every time and every state double must be BIT-EQUAL to the oracle's (array_equal), so that
+    a 1-ulp drift cannot hide behind the tolerance."""
     assert np.array_equal(ora.cells(), dev.cells(replica)), "cell assignment"
     for down in (False, True):
         a, b = ora.nbors(down), dev.nbors(replica, down)
@@ -57,7 +59,8 @@ def compare_engines(ora, dev, replica=0, n_events=0, time_rtol=1e-12):
     tb, nb, cb = dev.calendar(replica)
     assert np.array_equal(na, nb), "next-event partner"
     assert np.array_equal(ca, cb), "next-event type"
-    np.testing.assert_allclose(tb, ta, rtol=time_rtol, atol=0)
+    np.testing.assert_allclose(tb, ta, rtol=time_rtol, atol=0)  # the stated bar ...
+    assert np.array_equal(tb, ta), "calendar times are not bit-equal"  # ... and the one the engine is held to
     if n_events:
         ora.run(n_events)
         dev.run(n_events)
@@ -67,11 +70,29 @@ def compare_engines(ora, dev, replica=0, n_events=0, time_rtol=1e-12):
             bad = np.nonzero(la[f] != lb[f])[0]
             assert bad.size == 0, "event sequence differs in %s at event %d: %s vs %s" % (f, bad[0], la[bad[0]], lb[bad[0]])
         np.testing.assert_allclose(lb["t"], la["t"], rtol=time_rtol, atol=1e-300)
+        assert np.array_equal(lb["t"], la["t"]), "event times are not bit-equal"
         sa, sb = ora.state(), dev.state(replica)
-        np.testing.assert_allclose(sb["sv"], sa["sv"], rtol=1e-12, atol=1e-15)
+        assert np.array_equal(sb["sv"], sa["sv"]), "positions / velocities are not bit-equal"
+        assert sa["t"] == sb["t"] and sa["tfalse"] == sb["tfalse"]
         for f in ("bptnr", "identity", "extra_repuls"):
             assert np.array_equal(sa[f], sb[f]), f
         assert sa["coll"] == sb["coll"]
+
+
+def audit_nc(ora, dev=None, replica=0, make_oracle=None):
+    """check_nc_int.f:21-360 (main.F90:425, 1199): the reference's own audit of the H-bond <-> auxiliary-shoulder state
+    machine, on the oracle's state and -- through a second oracle instance that ADOPTS the device's read-back state and
+    lists -- on the device's.  boundbad == unboundbad == 0, no "no ss" complaint, m_ss == n_ss (the Fortran exits
+    otherwise)."""
+    a = ora.check_nc_int()
+    assert a["boundbad"] == 0 and a["unboundbad"] == 0 and a["no_ss"] == 0 and a["m_ss"] == a["n_ss"], a
+    if dev is not None:
+        aud = make_oracle()
+        aud.adopt_state(dev.state(replica), dev.nbors(replica))
+        b = aud.check_nc_int()
+        assert b == a, (a, b)
+        assert not aud.checkover()[0]
+    return a
 
 
 def check_run_until_output(tab, engines, lib_path=None):

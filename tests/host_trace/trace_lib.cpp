@@ -112,6 +112,18 @@ inline void run_init(const dmd::DevArrays& d, int r0, int nrep, const double* sv
     rep_save(r);
   }
 }
+inline int sheet_max_chains() { return 1 << 20; }
+inline void run_sheets(const dmd::DevArrays& d, int32_t* out) {
+  using namespace dmd;
+  const int nc = d.sys->N / d.sys->numbeads[0];
+  std::vector<uint8_t> hb((size_t)nc * nc);
+  std::vector<int32_t> lab(nc);
+  for (int rid = 0; rid < d.n_replicas; rid++) {
+    Rep r;
+    rep_bind(r, d, staged_global(d), nullptr, rid);
+    sheet_observables(r, out + 8 * (size_t)rid, hb.data(), lab.data());
+  }
+}
 inline void run_pack(const dmd::DevArrays& d, double* sv, int32_t* bp) {
   const size_t n = (size_t)d.n_replicas * d.n_beads;
   for (size_t k = 0; k < n; k++) {

@@ -6,7 +6,7 @@ overlaps (checkover.f) and run-to-run determinism."""
 import numpy as np
 import pytest
 
-from conftest import compare_engines
+from conftest import audit_nc, compare_engines
 from oracle.binding import OracleDMD
 from parallel_dmd_for_biomolecules_b200 import genconfig, tables
 from parallel_dmd_for_biomolecules_b200.dmd import DMD, DMDError, device_fill
@@ -23,11 +23,14 @@ def _pair(p, topo, tab, sv, bptnr=None):
 
 
 @pytest.mark.parametrize("engine", [1, 2])  # 1 = warp per replica, 2 = CTA per replica with batched commit
-@pytest.mark.parametrize("which,canon,n_events", [("A", False, 20000), ("A", True, 50000), ("B", False, 20000), ("B", True, 100000)])
+@pytest.mark.parametrize("which,canon,n_events", [("A", False, 20000), ("A", True, 50000), ("B", False, 20000), ("B", True, 100000),
+                                                  ("A018", True, 60000)])
 def test_event_sequence_matches_oracle(tab, system_a, system_b, which, canon, n_events, engine):
-    topo, sv, boxl = system_a if which == "A" else system_b
-    p = tables.make_params(boxl=boxl, tstar=0.5 if which == "A" else 0.18, canon=canon, n_replicas=5, log_capacity=n_events,
-                           engine=engine)
+    """A = BASELINE config 1, the shipped snapshot (at the T* = 0.5 it was generated for, and -- "A018" -- at the
+    temp_018 setup the config names: T* = 0.18, canon); B = config 2."""
+    topo, sv, boxl = system_b if which == "B" else system_a
+    tstar = {"A": 0.5, "B": 0.18, "A018": 0.18}[which]
+    p = tables.make_params(boxl=boxl, tstar=tstar, canon=canon, n_replicas=5, log_capacity=n_events, engine=engine)
     ora, dev = _pair(p, topo, tab, sv)
     compare_engines(ora, dev, replica=0, n_events=n_events)
     ea, eb = ora.energy(), dev.energy(0)
@@ -38,7 +41,7 @@ def test_event_sequence_matches_oracle(tab, system_a, system_b, which, canon, n_
     assert (sa.ghosts, sa.updates, sa.forced_updates) == (sb.ghosts, sb.updates, sb.forced_updates)
     assert abs(sb.nbr_visits / sa.nbr_visits - 1.0) < 0.05  # work counters (roofline input): the oracle counts a cascaded bead per request
     if canon:  # replica 3 draws from another RNG stream: compare it with its own oracle
-        p3 = tables.make_params(boxl=boxl, tstar=0.5 if which == "A" else 0.18, canon=True, log_capacity=n_events, seed=p.seed + 3)
+        p3 = tables.make_params(boxl=boxl, tstar=tstar, canon=True, log_capacity=n_events, seed=p.seed + 3)
         o3 = OracleDMD(p3, topo, tab)
         o3.set_state(sv)
         o3.run(n_events)
@@ -57,6 +60,8 @@ def test_hbond_rich_trajectory_and_restart(tab, engine):
     compare_engines(ora, dev, n_events=n)
     st = ora.stats()
     assert min(st.nevents[14], st.nevents[15], st.nevents[16], st.nevents[20], st.nevents[24], st.nevents[26]) > 0
+    a = audit_nc(ora, dev, make_oracle=lambda: OracleDMD(p, topo, tab))  # check_nc_int.f on oracle AND device state
+    assert a["m_ss"] >= 2 and a["pairs15"] > a["m_ss"]
     ora.sync_positions()
     s = ora.state()
     assert (s["bptnr"] > 0).sum() >= 2

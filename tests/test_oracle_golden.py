@@ -168,3 +168,21 @@ def test_run_file_round_trip(tmp_path, system_a):
     assert open(src, "rb").read() == open(out, "rb").read()
     assert fileio.energy_line(12, 0.5, 6048.0, 6.0, 0, 1, 2, 0.5, 1.5, 10.0, 20.0) == \
         "             12      0.5000   6048.0000      6.0000       0       1       2      0.5000      1.5000     10.0000     20.0000"
+
+
+def test_check_nc_int_audit_holds_along_an_hbond_rich_run(tab):
+    """check_nc_int.f:21-360 (an oracle invariant the reference itself defines): along a run in which
+    hydrogen bonds form and break, every audit finds boundbad == unboundbad == 0, no missing shoulder set and
+    m_ss == n_ss -- the condition whose violation makes the Fortran exit (check_nc_int.f:352-355)."""
+    from conftest import audit_nc
+    from oracle.binding import OracleDMD
+    from parallel_dmd_for_biomolecules_b200 import genconfig
+    topo, sv = genconfig.generate_box(["AAAAAAAAAAAA"], [8], 45.0, 0.10, tab, seed=1)
+    o = OracleDMD(tables.make_params(boxl=45.0, tstar=0.10, canon=True, seed=11), topo, tab)
+    o.set_state(sv)
+    seen = 0
+    for _ in range(10):
+        o.run(60000)
+        seen = max(seen, audit_nc(o)["m_ss"])
+        assert not o.checkover()[0]
+    assert seen >= 4  # shoulder sets were switched on (N-C pairs inside their well), so the audit had something to check
