@@ -4,7 +4,7 @@
 Metric (BASELINE.json): DMD collision events/s per B200 (every processed calendar event, counted like the
 reference's `coll`, main.F90:639).  Workload at N=1: BASELINE config 2 -- the 48-peptide Abeta16-22 (KLVFFAE)
 PRIME20 box, N = 1344 beads, L = 158.54 A, T* = 0.18, Andersen thermostat on (-Dcanon) -- as an ensemble of R
-independent replicas resident on one GPU (two replicas per hardware warp, 16 lanes each, in lockstep; the replica
+independent replicas resident on one GPU (four replicas per hardware warp, 8 lanes each, in lockstep; the replica
 count is the one that fills the device in one wave next to the list-rebuild service CTAs of the same kernel,
 dmdb_device_fill).  N>1: BASELINE config 3 -- the same box count per GPU (weak scaling), but the replicas form
 11-temperature ladders (temp_018 ... temp_050, qfile/script.sh:11-18) whose members are striped across the GPUs, with
@@ -50,8 +50,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--replicas", type=int, default=0, help="replicas per GPU (0 = dmdb_device_fill: one 28-warp CTA (56 replicas) per "
-                    "SM minus the list-rebuild service CTAs, 7168 on a 148-SM B200)")
+    ap.add_argument("--replicas", type=int, default=0, help="replicas per GPU (0 = dmdb_device_fill: one 28-warp CTA (112 replicas) per "
+                    "SM minus the list-rebuild service CTAs, 13440 on a 148-SM B200)")
     ap.add_argument("--events", type=int, default=20000, help="calendar events per replica per step")
     ap.add_argument("--ref-events", type=int, default=400000, help="events per host thread per step (--impl reference)")
     ap.add_argument("--ladder", action="store_true", help="config 3 on one GPU too: 11-temperature ladders + exchange per step "
@@ -247,7 +247,7 @@ def aggregated_regime(tab, peak):
     boxl = float(fx["boxl"])
     topo, _ = genconfig.system_b(tab, TSTAR, seed=1, boxl=boxl)
     # an aggregated box rebuilds its lists ~5 x slower than a dilute one (a bead has many more candidates): the measured
-    # optimum is 44 list-rebuild service CTAs beside 104 event-loop CTAs (20 / 128 for the dilute headline)
+    # optimum is 44 list-rebuild service CTAs beside 104 event-loop CTAs (28 / 120 for the dilute headline)
     import torch
     service = 44
     fill_r, fill_s = device_fill(0)
@@ -354,6 +354,9 @@ def main():
     tab = tables.load_default_tables()
     topo, sv = genconfig.system_b(tab, TSTAR, seed=1)
     fill_replicas, service_ctas = device_fill(local_rank)
+    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    per_cta = fill_replicas // (sms - service_ctas)  # replicas per 28-warp event-loop CTA as dmdb_device_fill sizes them
+    per_warp = per_cta // 28
     if args.replicas <= 0:
         args.replicas = fill_replicas
     N, R, E = topo.n_beads, args.replicas, args.events
@@ -452,10 +455,11 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD if not ladder else WORKLOAD_LADDER, "replicas_per_gpu": R, "beads_per_replica": N,
                        "events_per_replica_per_step": E,
-                       "parallelism": "two replicas per hardware warp (16 lanes each, lockstep), %d replicas per GPU, %d GPU(s)%s; "
+                       "parallelism": "%d replicas per hardware warp (%d lanes each, in lockstep), %d replicas per GPU, %d GPU(s)%s; "
                                       "per GPU %d event-loop CTAs + %s list-rebuild service CTAs in ONE kernel" % (
-                           R, world, ", dmdb_exchange (ncclAllGather + device-side decision + retemp) per step" if ladder else "",
-                           (R + 55) // 56, service_ctas if R == fill_replicas else "auto"),
+                           per_warp, 32 // per_warp, R, world,
+                           ", dmdb_exchange (ncclAllGather + device-side decision + retemp) per step" if ladder else "",
+                           (R + per_cta - 1) // per_cta, service_ctas if R == fill_replicas else "auto"),
                        "exchange": None if not ladder else {
                            "ladders": xch["ladders"], "ladder_size": len(replica_exchange.LADDER),
                            "pairs_attempted_per_step": xch["attempted"] / args.steps,

@@ -32,7 +32,8 @@
 //   dmd::w32 (inline: plain dmd:: names)  32 lanes per replica -- CTA-per-replica and whole-GPU engines, bulk kernels
 //   dmd::evl                              DMD_EVL_W lanes per replica -- the warp-per-replica event loop (engine 1)
 #ifndef DMD_EVL_W
-#define DMD_EVL_W 16  // two replicas per hardware warp (measured on B200, 48-peptide box: see DESIGN.md section 4)
+#define DMD_EVL_W 8  // four replicas per hardware warp (measured on B200, 48-peptide box, tools/prof_run.py: 32 lanes per
+                     // replica 2.15e8, 16: 2.55e8, 8: 2.77e8 events/s)
 #endif
 #define DMD_W 32
 #define DMD_VARIANT_BEGIN inline namespace w32 {
@@ -46,10 +47,12 @@
 #define DMD_W DMD_EVL_W
 #define DMD_VARIANT_BEGIN namespace evl {
 #define DMD_VARIANT_END }
-#include "dmd_engine.h"
-#if DMD_EVL_W == 16
-#include "dmd_lockstep.h"  // the hot path of two replicas per hardware warp, executed in lockstep
+#if DMD_EVL_W == 8  // four replicas per warp: 112 cascade queues per CTA must fit the static shared memory
+#undef DMD_CQ_CAP
+#define DMD_CQ_CAP 56
 #endif
+#include "dmd_engine.h"
+#include "dmd_lockstep.h"  // the hot path of 32 / DMD_EVL_W replicas per hardware warp, executed in lockstep
 #undef DMD_W
 #undef DMD_VARIANT_BEGIN
 #undef DMD_VARIANT_END
@@ -264,8 +267,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, DMD_MIN_CTAS) dmd_event_lo
   const evl::Staged tab = stage_consts_t<evl::Staged>(d, &sm.consts);
   const int wl = (int)threadIdx.x / DMD_EVL_W;  // this replica's slot in the CTA (DMD_EVL_W lanes each)
   const int w = ((int)blockIdx.x - n_srv) * EVL_RPC + wl;
-#if DMD_EVL_W == 16
-  const bool pair = __all_sync(0xffffffffu, w < nrep);  // both halves of this hardware warp hold a replica
+#if DMD_EVL_W < 32
+  const bool pair = __all_sync(0xffffffffu, w < nrep);  // every lane group of this hardware warp holds a replica
 #endif
   if (w >= nrep) return;
   const int rid = r0 + w;
@@ -284,8 +287,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, DMD_MIN_CTAS) dmd_event_lo
   }
   evl::Warp::sync();
 #endif
-#if DMD_EVL_W == 16
-  if (pair) evl::lk_run_events(r, n_events, (flags & 1) != 0);  // two replicas per warp in lockstep
+#if DMD_EVL_W < 32
+  if (pair) evl::lk_run_events(r, n_events, (flags & 1) != 0);  // the replicas of the warp in lockstep
   else if (r.error == 0) evl::run_events(r, n_events, (flags & 1) != 0);
 #else
   if (r.error == 0) evl::run_events(r, n_events, (flags & 1) != 0);
@@ -893,7 +896,11 @@ inline int sm_count() {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   return sms;
 }
-inline int default_service_ctas(int worker_ctas) { return worker_ctas >= 32 ? (worker_ctas * 10 + 32) / 64 : 0; }
+// one service CTA per 6.4 event-loop CTAs with one or two replicas per warp, per 4.3 with four (an event-loop CTA then
+// processes ~1.5 x the events and asks for as many more rebuilds): 120 + 28 CTAs on a 148-SM B200
+inline int default_service_ctas(int worker_ctas) {
+  return worker_ctas >= 32 ? (worker_ctas * (dmd::EVL_RPW >= 4 ? 15 : 10) + 32) / 64 : 0;
+}
 inline void device_fill(int& replicas, int& service) {
   const int sms = sm_count();
   int w = sms;
@@ -1105,10 +1112,11 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
         CUDA_OK(cudaStreamSynchronize(g_stream));
         CUDA_OK(cudaMemcpyFromSymbol(c, evl::g_phase_cyc, sizeof(c)));
         const double ev = (double)nrep * (double)arg;
-        static const char* nm[8] = {"flush", "pop", "pair_event", "main pass", "cascade prep", "cascade pass", "cold", "loop"};
+        static const char* nm[12] = {"flush", "pop", "event dynamics", "main pass", "cascade prep", "cascade pass", "interval/output",
+                                     "loop", "H-bond event", "ghost event", "wait for partner", "wait for service"};
         double tot = 0;
-        for (int k = 0; k < 8; k++) tot += (double)c[k];
-        for (int k = 0; k < 8; k++) fprintf(stderr, "phase %-13s %9.1f cycles/event  %5.1f %%\n", nm[k], c[k] / ev, 100.0 * c[k] / tot);
+        for (int k = 0; k < 12; k++) tot += (double)c[k];
+        for (int k = 0; k < 12; k++) fprintf(stderr, "phase %-16s %9.1f cycles/event  %5.1f %%\n", nm[k], c[k] / ev, 100.0 * c[k] / tot);
         fprintf(stderr, "phase total         %9.1f cycles/event\n", tot / ev);
       }
 #endif

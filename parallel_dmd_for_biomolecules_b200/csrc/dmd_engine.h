@@ -1765,7 +1765,9 @@ DMD_COLD void interval_event_cold(Rep r) {
 #if !defined(DMD_HOST_TRACE)
     if (r.svc) {  // hand nbor() + events() to a service CTA (another SM); the view's scalars travel through r.sc
       rep_save(r);
+      DMD_PROF_MARK(r, 6);
       in_place = !svc_request(r);
+      DMD_PROF_MARK(r, 11);  // waiting for the list-rebuild service
       r.error = r.sc->error;  // a service CTA reports list overflow etc. through the stored scalars
       r.error_info = r.sc->error_info;
     }

@@ -18,38 +18,51 @@
 // event at the head of its calendar (H-bond events, ghost, interval incl. list rebuild, output; a few per cent of
 // the events), BOTH process their event through the serial engine code and meet again at the next vote.
 // Results are those of the serial code: same items, same order of compare-and-lower operations, same tie rules.
-#if DMD_W != 16 || defined(DMD_HOST_TRACE)
-#error "dmd_lockstep.h is the two-replicas-per-warp hot path: include it in the 16-lane device build only"
+#if (DMD_W != 16 && DMD_W != 8) || defined(DMD_HOST_TRACE)
+#error "dmd_lockstep.h is the several-replicas-per-warp hot path: include it in the 16- or 8-lane device build only"
 #endif
 
 namespace dmd {
 DMD_VARIANT_BEGIN
 
+// LK_W lanes per replica, LK_SUB replicas ("subs") per hardware warp
+constexpr int LK_W = DMD_W, LK_SUB = 32 / DMD_W;
+constexpr unsigned LK_MASK = (1u << LK_W) - 1u;
 struct Lk {
-  static __device__ __forceinline__ int lane() { return threadIdx.x & 15; }
-  static __device__ __forceinline__ int half() { return (threadIdx.x >> 4) & 1; }
+  static __device__ __forceinline__ int lane() { return threadIdx.x & (LK_W - 1); }
+  static __device__ __forceinline__ int half() { return (threadIdx.x >> WLOG) & (LK_SUB - 1); }  // which replica of the warp
   static __device__ __forceinline__ void sync() { __syncwarp(); }
-  // bit k = lane k of the caller's half
-  static __device__ __forceinline__ unsigned ballot(bool p) { return (__ballot_sync(0xffffffffu, p) >> (threadIdx.x & 16u)) & 0xffffu; }
-  static __device__ __forceinline__ int shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src, 16); }
-  static __device__ __forceinline__ bool any2(bool p) { return __any_sync(0xffffffffu, p); }  // over BOTH replicas
+  // bit k = lane k of the caller's replica
+  static __device__ __forceinline__ unsigned ballot(bool p) {
+    return (__ballot_sync(0xffffffffu, p) >> (threadIdx.x & 31u & ~(unsigned)(LK_W - 1))) & LK_MASK;
+  }
+  static __device__ __forceinline__ int shfl(int v, int src) { return __shfl_sync(0xffffffffu, v, src, LK_W); }
+  static __device__ __forceinline__ bool any2(bool p) { return __any_sync(0xffffffffu, p); }  // over ALL replicas of the warp
   static __device__ __forceinline__ bool all2(bool p) { return __all_sync(0xffffffffu, p); }
   static __device__ __forceinline__ unsigned max2(unsigned v) { return __reduce_max_sync(0xffffffffu, v); }
-  // minimum over the lanes of the caller's half: one REDUX per half, the other half's lanes neutralised
+  // minimum over the lanes of the caller's replica: one REDUX per replica of the warp, the others' lanes neutralised
   static __device__ __forceinline__ unsigned hmin(unsigned v) {
     const int h = half();
-    const unsigned a = __reduce_min_sync(0xffffffffu, h == 0 ? v : 0xffffffffu);
-    const unsigned b = __reduce_min_sync(0xffffffffu, h == 1 ? v : 0xffffffffu);
-    return h ? b : a;
+    unsigned res = 0;
+#pragma unroll
+    for (int s = 0; s < LK_SUB; s++) {
+      const unsigned m = __reduce_min_sync(0xffffffffu, h == s ? v : 0xffffffffu);
+      if (h == s) res = m;
+    }
+    return res;
   }
-  // minimum over the lanes of the caller's half that are in the caller's group (0 or 1)
+  // minimum over the lanes of the caller's replica that are in the caller's group (16-lane build: two groups)
   static __device__ __forceinline__ unsigned gmin(unsigned v, int grp) {
+#if DMD_W == 16
     const int s = half() * 2 + grp;
     const unsigned m0 = __reduce_min_sync(0xffffffffu, s == 0 ? v : 0xffffffffu);
     const unsigned m1 = __reduce_min_sync(0xffffffffu, s == 1 ? v : 0xffffffffu);
     const unsigned m2 = __reduce_min_sync(0xffffffffu, s == 2 ? v : 0xffffffffu);
     const unsigned m3 = __reduce_min_sync(0xffffffffu, s == 3 ? v : 0xffffffffu);
     return s < 2 ? (s == 0 ? m0 : m1) : (s == 2 ? m2 : m3);
+#else
+    return hmin(v);  // one bead per replica and pass: no groups
+#endif
   }
 };
 
@@ -97,7 +110,7 @@ DMD_DEV void lk_flush_dirty(Rep& r) {
     const int g1 = dirty0 ? pop_lowest_bit(dirty0) : -1;
     double x0 = T_PAD, x1 = T_PAD;
 #pragma unroll
-    for (int q = lane; q < 32; q += 16) {
+    for (int q = lane; q < 32; q += LK_W) {
       const double y0 = have ? r.cal[g0 * 32 + q].t : T_PAD;
       const double y1 = g1 >= 0 ? r.cal[g1 * 32 + q].t : T_PAD;
       x0 = y0 < x0 ? y0 : x0;
@@ -119,7 +132,7 @@ DMD_DEV int lk_pop_min(Rep& r, CalEnt& ev) {
   const int lane = Lk::lane();
   unsigned long long best = ord_bits64(T_PAD);
   int bg = 0x7fffffff;
-  for (int g = lane; g < r.G; g += 16) {
+  for (int g = lane; g < r.G; g += LK_W) {
     const unsigned long long v = r.tmin1[g];
     if (v < best) {  // ascending g: the first minimum keeps the lowest group
       best = v;
@@ -134,7 +147,7 @@ DMD_DEV int lk_pop_min(Rep& r, CalEnt& ev) {
   double v = T_PAD;
   int key = 0x7fffffff, pt = -1, ty = -1;
 #pragma unroll
-  for (int q = lane; q < 32; q += 16) {
+  for (int q = lane; q < 32; q += LK_W) {
     const CalEnt e = r.cal[sg * 32 + q];
     if (e.t < v) {
       v = e.t;
@@ -147,7 +160,7 @@ DMD_DEV int lk_pop_min(Rep& r, CalEnt& ev) {
   ord_split(v, vhi, vlo);
   int wkey = key;
   lk_hargmin_ord(vhi, vlo, wkey);
-  const int src = wkey & 15;  // the lane that scanned the winning entry holds it as its own best
+  const int src = wkey & (LK_W - 1);  // the lane that scanned the winning entry holds it as its own best
   pt = Lk::shfl(pt, src);
   ty = Lk::shfl(ty, src);
   ev.t = ord_join(vhi, vlo);
@@ -167,7 +180,7 @@ DMD_DEV void lk_pass(Rep& r, const int mode, const bool act, const int i, const 
   const int cap = r.cap;
   int a, q0, ssh, nu, nd, er3, skip, T, grp = 0;
   bool lact = act;
-  unsigned segmask = 0xffffu;  // the lanes of this replica (bit k = lane k) that work for the same bead as this lane
+  unsigned segmask = LK_MASK;  // the lanes of this replica (bit k = lane k) that work for the same bead as this lane
   uint32_t e0 = 0, ma;
   BeadRec ra;
   if (mode != 2) {  // ---- main pass (same items as prediction_pass: see there)
@@ -191,22 +204,22 @@ DMD_DEV void lk_pass(Rep& r, const int mode, const bool act, const int i, const 
       atomicAdd(&c[1], (unsigned)(nu + nd));
     }
     q0 = lane;
-    ssh = 4;
+    ssh = WLOG;
     skip = mode == 1 ? i : -1;
     {  // the entry of the lane's first item
       const bool isup = q0 < nu;
-      const int src = (isup ? q0 : q0 - nu) & 15;
+      const int src = (isup ? q0 : q0 - nu) & (LK_W - 1);
       const uint32_t t0 = (uint32_t)Lk::shfl((int)s0, src), t1 = (uint32_t)Lk::shfl((int)s1, src);
       e0 = isup ? t0 : t1;
     }
-  } else {  // ---- cascade pass: one bead on 16 lanes, or two on 8 lanes each
-    const int sh = rem >= 2 ? 1 : 0;  // rem is this replica's own queue length; an idle replica has rem <= 0
-    const int SEG = 16 >> sh;
-    const int g = lane >> (4 - sh);
-    segmask = (sh == 0 ? 0xffffu : 0xffu) << (g * SEG);
+  } else {  // ---- cascade pass: one bead on all lanes of the replica, or (16-lane build) two on 8 lanes each
+    const int sh = (LK_W == 16 && rem >= 2) ? 1 : 0;  // rem is this replica's own queue length; an idle replica has rem <= 0
+    const int SEG = LK_W >> sh;
+    const int g = lane >> (WLOG - sh);
+    segmask = (sh == 0 ? LK_MASK : ((1u << SEG) - 1u)) << (g * SEG);
     grp = g;
     q0 = lane & (SEG - 1);
-    ssh = 4 - sh;
+    ssh = WLOG - sh;
     lact = act && g < rem;
     a = lact ? r.cq[idx + g] : 0;
     if (q0 < cap) e0 = r.up[(size_t)a * cap + q0];
@@ -331,7 +344,7 @@ DMD_DEV void lk_partial_events(Rep& r, const int i, const int j, const bool xpul
     Lk::sync();  // later passes re-read the entries this one may have lowered
     DMD_PROF_MARK(r, mode < 2 ? 3 : 5);
     if (mode == 2) {
-      if (pact) idx += rem >= 2 ? 2 : 1;
+      if (pact) idx += (LK_W == 16 && rem >= 2) ? 2 : 1;
     } else {
       mode = (mode == 0 && Lk::any2(act && j >= 0)) ? 1 : 2;
       if (mode == 2) {  // all down items are done: prepare the cascade queue (each replica for itself, 16-lane code)
@@ -341,7 +354,7 @@ DMD_DEV void lk_partial_events(Rep& r, const int i, const int j, const bool xpul
         }
         if (cqn > 1) {  // a bead queued by both i and j is re-predicted once
           int keep_n = 0;
-          for (int base = 0; base < cqn; base += 16) {
+          for (int base = 0; base < cqn; base += LK_W) {
             const int k = base + Warp::lane();
             bool keep = false;
             int v = -1;
@@ -390,11 +403,14 @@ DMD_DEV void lk_process(Rep& r, const int o, const CalEnt& ev) {
     ct = event_dynamics_hot(r.c, ct, code, ri, rj, r.c.meta[pi], ri.bptnr == pj, r.tfalse);
   } else if (o < r.N) {  // H-bond related pair event: resolution, eventdyn, bookkeeping (cold, out of line)
     code = overlay_code(sc_of(ev.type), pi, r.rec[pi], pj, r.rec[pj]);
+    DMD_PROF_MARK(r, 2);
     const ColdRes cr = pair_event_cold(r, pi, pj, ct, code);
     ct = cr.ct;
     xpulse_del = cr.xpulse != 0;
     r.ctr = cr.ctr;
+    DMD_PROF_MARK(r, 8);
   } else {  // pseudo-events
+    DMD_PROF_MARK(r, 2);
     rep_save(r);
     if (o == r.N) {
       pi = ghost_event_cold(r, prev_tfalse);
@@ -409,9 +425,11 @@ DMD_DEV void lk_process(Rep& r, const int o, const CalEnt& ev) {
     clear_dirty(r);
     Warp::sync();
     if (redo) mark_dirty(r, r.N >> 5);  // the next ghost time
-    DMD_PROF_MARK(r, 6);
+    DMD_PROF_MARK(r, o == r.N ? 9 : 6);
   }
+  DMD_PROF_MARK(r, 2);
   Lk::sync();  // every lane has read the two records
+  DMD_PROF_MARK(r, 10);  // (waiting for the warp's other replica)
   if (o < r.N) {
     if (hot && Lk::lane() == 0) {
       BeadRec* qi = &r.rec[pi];

@@ -272,7 +272,7 @@ def test_frozen_event_sequence(tab, system_a, system_b, which, engine):
 
 def test_device_fill_matches_the_launch(tab):
     replicas, service = device_fill(0)
-    per_cta = 56  # 28 hardware warps per event-loop CTA, two replicas (16 lanes each) per warp
+    per_cta = 112  # 28 hardware warps per event-loop CTA, four replicas (8 lanes each) per warp
     assert replicas > 0 and replicas % per_cta == 0 and service >= 0
     import torch
     sms = torch.cuda.get_device_properties(0).multi_processor_count
