@@ -279,8 +279,15 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, DMD_MIN_CTAS) dmd_event_lo
     r.svc_ctl = d.svc_ctl;
   }
 #if defined(DMD_PHASE_PROF)
+#if DMD_EVL_W >= 16
   __shared__ unsigned long long s_prof[EVL_RPC][16];
   r.prof = s_prof[wl];
+#else  // no room beside the cascade queues: the accumulators sit in global memory (they stay in L1 / L2)
+  __shared__ unsigned long long* s_prof_base;
+  if (threadIdx.x == 0) s_prof_base = evl::g_phase_acc + (size_t)blockIdx.x * EVL_RPC * 16;
+  __syncthreads();
+  r.prof = s_prof_base + wl * 16;
+#endif
   if (evl::Warp::lane() == 0) {
     for (int k = 0; k < 15; k++) r.prof[k] = 0;
     r.prof[15] = (unsigned long long)clock64();
@@ -896,10 +903,13 @@ inline int sm_count() {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   return sms;
 }
-// one service CTA per 6.4 event-loop CTAs with one or two replicas per warp, per 4.3 with four (an event-loop CTA then
-// processes ~1.5 x the events and asks for as many more rebuilds): 120 + 28 CTAs on a 148-SM B200
+// one service CTA per 6.4 event-loop CTAs with one or two replicas per warp, per 5.2 with four (an event-loop CTA then
+// processes ~1.5 x the events and asks for as many more rebuilds): 124 + 24 CTAs on a 148-SM B200.  Measured on the
+// headline workload (tools/svc_sweep.py): 22: 2.80e8, 23: 2.98e8, 24: 2.98e8, 26: 2.94e8, 28: 2.91e8 events/s -- too few
+// service CTAs cost far more (requests queue up, time out and are rebuilt in place) than too many
 inline int default_service_ctas(int worker_ctas) {
-  return worker_ctas >= 32 ? (worker_ctas * (dmd::EVL_RPW >= 4 ? 15 : 10) + 32) / 64 : 0;
+  if (worker_ctas < 32) return 0;
+  return dmd::EVL_RPW >= 4 ? (worker_ctas * 25 + 64) / 128 : (worker_ctas * 10 + 32) / 64;
 }
 inline void device_fill(int& replicas, int& service) {
   const int sms = sm_count();

@@ -41,6 +41,7 @@ constexpr int CQ_Q = CQ_CAP - 8;    // ... of CQ_Q entries (<= one per down-list
 // SM clocks since its previous mark to a per-warp shared-memory slot; the kernel sums the slots into g_phase_cyc
 #if defined(DMD_PHASE_PROF) && !defined(DMD_HOST_TRACE)
 __device__ unsigned long long g_phase_cyc[16];
+__device__ unsigned long long g_phase_acc[160 * 4 * 28 * 16];  // per-replica accumulators of the 8-lane build
 #define DMD_PROF_MARK(r, k)                                                    \
   do {                                                                         \
     if ((r).prof && Warp::lane() == 0) {                                       \
