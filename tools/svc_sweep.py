@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Event-loop / list-rebuild-service split sweep on system B: for each service CTA count S the device is filled with
-(SMs - S) event-loop CTAs of replicas; prints events/s.  usage: svc_sweep.py S1,S2,... [events] [lib]"""
+(SMs - S) event-loop CTAs of replicas; prints events/s.  usage: svc_sweep.py S1,S2,... [events] [lib] [replicas per CTA]"""
 import os
 import sys
 
@@ -15,7 +15,7 @@ nev = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
 lib = sys.argv[3] if len(sys.argv) > 3 else None
 sms = torch.cuda.get_device_properties(0).multi_processor_count
 fr, fs = device_fill(0)
-per_cta = fr // (sms - fs)
+per_cta = int(sys.argv[4]) if len(sys.argv) > 4 else fr // (sms - fs)
 tab = tables.load_default_tables()
 topo, sv = genconfig.system_b(tab, 0.18, seed=1)
 for S in svc:
