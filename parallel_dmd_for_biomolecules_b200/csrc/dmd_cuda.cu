@@ -152,20 +152,49 @@ __device__ __noinline__ void svc_serve_in_kernel(DevArrays d, int r0, int nrep, 
   int32_t* const s_heads = reinterpret_cast<int32_t*>(scratch);
   int32_t* const s_cnext = s_heads + d.ncc3;
   uint32_t* const s_cpk = reinterpret_cast<uint32_t*>(s_cnext + d.n_beads);
-  const int scan0 = (int)(((long long)(blockIdx.x * DMD_SVC_GROUPS + grp) * nrep) / ((int)gridDim.x * DMD_SVC_GROUPS));
+  // Every group looks for requests in CIRCULAR order from its own starting point and takes the first one it meets, so
+  // that idle groups go for different requests (all of them taking the lowest pending index made them collide on one
+  // request and rescan).  Four flags per load, all loads of a thread in flight together.
+  const int32_t* const flags = d.svc_flag + r0;
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(flags) & 15) == 0;
+  const int nvec = vec_ok ? nrep >> 2 : 0;
+  const int scan0 = nvec ? (int)(((long long)(blockIdx.x * DMD_SVC_GROUPS + grp) * nvec) / ((int)gridDim.x * DMD_SVC_GROUPS)) : 0;
   while (true) {
     if (tid == 0) s_pick[grp] = 0x7fffffff;
     svc_group_sync(grp, gsz);
-    for (int k = tid; k < nrep; k += nt) {
-      int idx = k + scan0;
-      if (idx >= nrep) idx -= nrep;
-      if (*(volatile int32_t*)(d.svc_flag + r0 + idx) == 1) {
-        atomicMin(&s_pick[grp], idx);
-        break;
+    int found = 0x7fffffff;  // circular offset of the first pending request this thread saw
+    for (int k0 = tid; k0 < nvec; k0 += 4 * nt) {
+      int4 w[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        int v = k0 + u * nt + scan0;
+        v = v < nvec ? v : v - nvec;
+        w[u] = k0 + u * nt < nvec ? __ldcv(reinterpret_cast<const int4*>(flags) + v) : make_int4(0, 0, 0, 0);
       }
+#pragma unroll
+      for (int u = 3; u >= 0; u--) {
+        const int kb = (k0 + u * nt) * 4;
+        if (w[u].w == 1) found = kb + 3;
+        if (w[u].z == 1) found = kb + 2;
+        if (w[u].y == 1) found = kb + 1;
+        if (w[u].x == 1) found = kb;
+      }
+      if (found != 0x7fffffff) break;
     }
+    if (found == 0x7fffffff)
+      for (int k = nvec * 4 + tid; k < nrep; k += nt)  // the last nrep % 4 flags (or all of them: unaligned array)
+        if (*(volatile const int32_t*)(flags + k) == 1) {
+          found = k;
+          break;
+        }
+    if (found != 0x7fffffff) atomicMin(&s_pick[grp], found);
     svc_group_sync(grp, gsz);
-    const int pick = s_pick[grp];
+    int pick = s_pick[grp];
+    if (pick != 0x7fffffff && pick < nvec * 4) {  // circular offset -> replica
+      int v = (pick >> 2) + scan0;
+      v = v < nvec ? v : v - nvec;
+      pick = v * 4 + (pick & 3);
+    }
     if (tid == 0) {
       if (pick == 0x7fffffff) {
         const unsigned long long done = *(volatile unsigned long long*)&d.svc_ctl[0];
@@ -244,8 +273,9 @@ __device__ __noinline__ void svc_serve_in_kernel(DevArrays d, int r0, int nrep, 
         svc_group_sync(grp, gsz);
         evl::cell_clear(q, tid, nt);
       }
+      svc_group_sync(grp, gsz);  // predict_all_flat reads the rows other threads wrote
     }
-    for (int l = tid; l < q.N; l += nt) evl::redo_lane(q, l);  // events.f:23-107; the requester refreshes the group minima
+    evl::predict_all_flat(q, tid >> 5, nt >> 5);  // events.f:23-107; the requester refreshes the group minima
     if (q.error && evl::Warp::lane() == 0 && atomicCAS(&q.sc->error, 0, q.error) == 0) q.sc->error_info = q.error_info;
     __threadfence();
     svc_group_sync(grp, gsz);
@@ -903,13 +933,13 @@ inline int sm_count() {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   return sms;
 }
-// one service CTA per 6.4 event-loop CTAs with one or two replicas per warp, per 5.2 with four (an event-loop CTA then
-// processes ~1.5 x the events and asks for as many more rebuilds): 124 + 24 CTAs on a 148-SM B200.  Measured on the
-// headline workload (tools/svc_sweep.py): 22: 2.80e8, 23: 2.98e8, 24: 2.98e8, 26: 2.94e8, 28: 2.91e8 events/s -- too few
-// service CTAs cost far more (requests queue up, time out and are rebuilt in place) than too many
+// one service CTA per 6.4 event-loop CTAs with one or two replicas per warp, per 5.4 with four (an event-loop CTA then
+// processes ~1.5 x the events and asks for as many more rebuilds): 125 + 23 CTAs on a 148-SM B200.  Measured on the
+// headline workload (tools/svc_sweep.py): 18: 2.05e8, 20: 2.56e8, 22: 3.12e8, 24: 3.08e8 events/s -- too few service
+// CTAs cost far more (requests queue up, time out and are rebuilt in place) than too many
 inline int default_service_ctas(int worker_ctas) {
   if (worker_ctas < 32) return 0;
-  return dmd::EVL_RPW >= 4 ? (worker_ctas * 25 + 64) / 128 : (worker_ctas * 10 + 32) / 64;
+  return dmd::EVL_RPW >= 4 ? (worker_ctas * 47 + 128) / 256 : (worker_ctas * 10 + 32) / 64;
 }
 inline void device_fill(int& replicas, int& service) {
   const int sms = sm_count();

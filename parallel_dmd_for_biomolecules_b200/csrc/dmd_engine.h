@@ -776,6 +776,105 @@ DMD_DEV void redo_lane(Rep& r, int l) {
   r.cal[l] = ne;
 }
 
+#if !defined(DMD_HOST_TRACE)
+// events.f:23-107 for the list-rebuild service: the items of 32 consecutive beads are spread over the 32 lanes of a
+// hardware warp (one pair prediction per lane and trip) instead of one bead per lane -- a bead has 0 ... ~15 items, so
+// the per-bead loop of redo_lane() leaves more than half of the lanes idle.  Same items, same arithmetic, and the same
+// winner: the earliest time, ties to the item that comes first in the bead's own order (events.f:53 is a strict <).
+DMD_DEV void predict_all_flat(Rep& r, int warp, int nwarps) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, cap = r.cap;
+  const double best0 = r.interval_max + LTSTEP - r.tfalse;
+  for (int l0 = warp * 32; l0 < r.N; l0 += nwarps * 32) {
+    const int l = l0 + lane;
+    const bool valid = l < r.N;
+    const int ll = valid ? l : r.N - 1;
+    const int e1 = r.rec[ll].er1, e2 = r.rec[ll].er2, e3 = r.er34[2 * ll];
+    const int nu = valid ? (int)r.nup[ll] : 0;
+    const bool a0 = valid && e1 > l, a1 = valid && e2 > l, a2 = valid && e3 > l;  // events.f:77 (skips "none" = -1 too)
+    const int n = nu + (int)a0 + (int)a1 + (int)a2;
+    int inc = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(FULL, inc, d);
+      if (lane >= d) inc += v;
+    }
+    const int off = inc - n, T = __shfl_sync(FULL, inc, 31);
+    double best = best0;
+    int bj = -1, bty = -1;
+    for (int b = 0; b < T; b += 32) {
+      const int x = b + lane;
+      const bool have = x < T;
+      int o = 0;  // the lane whose bead owns item x: the largest o with off(o) <= x
+#pragma unroll
+      for (int st = 16; st >= 1; st >>= 1) {
+        const int v = __shfl_sync(FULL, off, o + st);
+        if (v <= x) o += st;
+      }
+      const int p = x - __shfl_sync(FULL, off, o), nuo = __shfl_sync(FULL, nu, o), lo = l0 + o;
+      const int oe1 = __shfl_sync(FULL, e1, o), oe2 = __shfl_sync(FULL, e2, o), oe3 = __shfl_sync(FULL, e3, o);
+      int j = -1, sc = 1;
+      if (have) {
+        if (p < nuo) {
+          const uint32_t e = r.up[(size_t)lo * cap + p];
+          j = (int)(e & NB_MASK);
+          sc = (int)(e >> NB_SHIFT);
+        } else {  // the (p - nu)-th auxiliary partner above the bead, in the order er1, er2, er3
+          int c = p - nuo;
+          if (oe1 > lo) { if (c == 0) j = oe1; c--; }
+          if (oe2 > lo) { if (c == 0) j = oe2; c--; }
+          if (oe3 > lo) { if (c == 0) j = oe3; c--; }
+        }
+      }
+      double tij = T_NONE;
+      int ty = -1;
+      if (j >= 0) {
+        const BeadRec ro = r.rec[lo], rj = r.rec[j];
+        const int code = overlay_code(sc, lo, ro, j, rj);
+        int type = -1;
+        pair_time(r.c, code, ro, rj, r.c.meta[lo], ro.bptnr == j, r.tfalse, tij, type);
+        ty = pack_type(type, sc);
+      }
+      // segmented arg-min scan over the lanes (items of one bead are neighbours); the left item wins a tie
+      unsigned hi, lw;
+      ord_split(tij, hi, lw);
+      int src = lane;
+      const int key = have ? o : 32 + lane;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned h2 = __shfl_up_sync(FULL, hi, d), w2 = __shfl_up_sync(FULL, lw, d);
+        const int s2 = __shfl_up_sync(FULL, src, d), k2 = __shfl_up_sync(FULL, key, d);
+        if (lane >= d && k2 == key && (h2 < hi || (h2 == hi && w2 <= lw))) {
+          hi = h2;
+          lw = w2;
+          src = s2;
+        }
+      }
+      // every lane, as the OWNER of its bead, reads the result at the last lane of its segment in this trip
+      const int seg_end = off + n < b + 32 ? off + n : b + 32;
+      const bool seg = n > 0 && seg_end > b && off < b + 32 && seg_end > off;
+      const int last = seg ? seg_end - 1 - b : 0;
+      const unsigned sh = __shfl_sync(FULL, hi, last), sw = __shfl_sync(FULL, lw, last);
+      const int ss = __shfl_sync(FULL, src, last);
+      const int cj = __shfl_sync(FULL, j, ss), cty = __shfl_sync(FULL, ty, ss);
+      const double ts = ord_join(sh, sw);
+      if (seg && ts < best) {  // strict: an earlier trip holds earlier items
+        best = ts;
+        bj = cj;
+        bty = cty;
+      }
+    }
+    if (valid) {
+      CalEnt ne;
+      ne.t = best + r.tfalse;
+      ne.ptnr = bj;
+      ne.type = bty;
+      r.cal[l] = ne;
+    }
+  }
+}
+#endif
+
 // events.f:23-123 for the whole replica (every bead is re-derived from interval_max + ltstep)
 DMD_DEV void predict_all(Rep& r) {
   Warp::sync();
@@ -1351,13 +1450,34 @@ DMD_DEV void chainwise_lists(Rep& r, const uint32_t* cpk, const unsigned* near, 
         nd++;
       }
     };
-    auto within = [&](int j, int sc) {  // nbor.f:97-105 with the cut-off of the static class
-      const BeadRec* pj = &r.rec[j];
-      double rx = rk.x - pj->x, ry = rk.y - pj->y, rz = rk.z - pj->z;
-      rx = rx - dmd_round(rx);
-      ry = ry - dmd_round(ry);
-      rz = rz - dmd_round(rz);
-      return rx * rx + ry * ry + rz * rz <= s.rlsq[sc];
+    // Two steps per chain, so that the lanes stay together and the gathers overlap: (1) the integer block test
+    // (cell words from shared memory, no global loads) marks the candidates in a bit mask; (2) the mask is drained four
+    // candidates at a time -- four position gathers in flight, then the class / distance rule (nbor.f:60, :97-105 with
+    // the cut-off of the static class) and the appends in ascending order.
+    auto drain = [&](unsigned long long cand, const int jbase, auto&& classify) {
+      while (cand) {
+        int jq[4], sq[4];
+        double d2[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          jq[q] = cand ? jbase + (__ffsll((long long)cand) - 1) : -1;
+          cand &= cand - 1ull;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int jj = jq[q] >= 0 ? jq[q] : kk;  // an always valid address: the loads are unconditional
+          sq[q] = classify(jj);
+          const BeadRec* pj = &r.rec[jj];
+          double rx = rk.x - pj->x, ry = rk.y - pj->y, rz = rk.z - pj->z;
+          rx = rx - dmd_round(rx);
+          ry = ry - dmd_round(ry);
+          rz = rz - dmd_round(rz);
+          d2[q] = rx * rx + ry * ry + rz * rz;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (jq[q] >= 0 && (code_is_bonded_class(sq[q]) || d2[q] <= s.rlsq[sq[q]])) append(jq[q], sq[q]);
+      }
     };
     // (a) own chain
     {
@@ -1365,15 +1485,15 @@ DMD_DEV void chainwise_lists(Rep& r, const uint32_t* cpk, const unsigned* near, 
       const int own_lo = kk - meta_local(mk);
       const uint8_t* const sct_row = r.c.sctab + s.sct_off[sp] + (size_t)meta_local(mk) * nb;
       const int nbmax = s.numbeads[0] > s.numbeads[1] ? s.numbeads[0] : s.numbeads[1];
+      unsigned long long cand = 0ull;
 #pragma unroll 4
       for (int lj = 0; lj < nbmax; lj++) {
-        const int j = own_lo + lj;
-        if (!live || lj >= nb || j == k) continue;
+        const int j = own_lo + (lj < nb ? lj : 0);
         const uint32_t pj = cpk[j];
-        if (pj == CPK_OUT || !in_fine_stencil(pk, pj, ncr)) continue;
-        const int sc = (int)sct_row[lj];
-        if (code_is_bonded_class(sc) || within(j, sc)) append(j, sc);  // nbor.f:60 / :97-105
+        const bool ok = live && lj < nb && j != k && pj != CPK_OUT && in_fine_stencil(pk, pj, ncr);
+        cand |= (unsigned long long)ok << lj;
       }
+      drain(cand, own_lo, [&](int j) { return (int)sct_row[j - own_lo]; });
     }
     // (b) the chains near the own one: the union over the hardware warp keeps the loops in step
     unsigned m0 = live ? near[2 * ck] : 0u, m1 = live ? near[2 * ck + 1] : 0u;
@@ -1387,15 +1507,14 @@ DMD_DEV void chainwise_lists(Rep& r, const uint32_t* cpk, const unsigned* near, 
         const int c = half * 32 + bit;
         const bool mine = (mine_mask >> bit) & 1u;
         const int f = (chain_first)(s, c), nb = (chain_len)(s, c);
+        unsigned long long cand = 0ull;
 #pragma unroll 4
-        for (int lj = 0; lj < nb; lj++) {  // (unrolled: the cell words of four candidates are in flight together)
-          const int j = f + lj;
-          if (!mine) continue;
-          const uint32_t pj = cpk[j];
-          if (pj == CPK_OUT || !in_fine_stencil(pk, pj, ncr)) continue;
-          const int sc = static_code(s, mk, ck, k, r.c.meta[j], c, j);  // other chain: 1, 15 or 16
-          if (within(j, sc)) append(j, sc);
+        for (int lj = 0; lj < nb; lj++) {
+          const uint32_t pj = cpk[f + lj];
+          const bool ok = mine && pj != CPK_OUT && in_fine_stencil(pk, pj, ncr);
+          cand |= (unsigned long long)ok << lj;
         }
+        drain(cand, f, [&](int j) { return static_code(s, mk, ck, k, r.c.meta[j], c, j); });  // other chain: 1, 15 or 16
       }
     }
     if (valid) {
