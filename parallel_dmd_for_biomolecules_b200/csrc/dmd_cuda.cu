@@ -933,13 +933,16 @@ inline int sm_count() {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   return sms;
 }
-// one service CTA per 6.4 event-loop CTAs with one or two replicas per warp, per 5.4 with four (an event-loop CTA then
-// processes ~1.5 x the events and asks for as many more rebuilds): 125 + 23 CTAs on a 148-SM B200.  Measured on the
-// headline workload (tools/svc_sweep.py): 18: 2.05e8, 20: 2.56e8, 22: 3.12e8, 24: 3.08e8 events/s -- too few service
-// CTAs cost far more (requests queue up, time out and are rebuilt in place) than too many
+// one service CTA per 6.4 event-loop CTAs with one or two replicas per warp, per 5.2 with four (an event-loop CTA then
+// processes ~1.5 x the events and asks for as many more rebuilds): 124 + 24 CTAs on a 148-SM B200.  Measured on the
+// headline workload (tools/prof_run.py, 40 000 events per replica after 60 000): 20: 2.36e8, 23: 2.78e8, 24: 3.09e8,
+// 25: 2.80e8, 26: 3.05e8, 27: 2.84e8, 28: 3.01e8, 30: 2.98e8 events/s.  Too few service CTAs cost far more than too many
+// (requests queue up, time out and are rebuilt in place), and the count must be EVEN: the two SMs of a TPC get
+// consecutive CTAs, an odd count puts one event-loop CTA next to a service CTA, that CTA runs ~9 % slower than the
+// others (it shares the TPC's instruction cache with the rebuild code) and the launch ends when the last CTA does.
 inline int default_service_ctas(int worker_ctas) {
   if (worker_ctas < 32) return 0;
-  return dmd::EVL_RPW >= 4 ? (worker_ctas * 47 + 128) / 256 : (worker_ctas * 10 + 32) / 64;
+  return ((dmd::EVL_RPW >= 4 ? (worker_ctas * 25 + 64) / 128 : (worker_ctas * 10 + 32) / 64) + 1) & ~1;
 }
 inline void device_fill(int& replicas, int& service) {
   const int sms = sm_count();
@@ -1126,7 +1129,7 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
           n_srv = want < sms - 1 ? want : sms - 1;
         } else if (grid_evl <= sms) {  // one wave: as many service CTAs as fit beside the event-loop CTAs
           const int want = default_service_ctas(grid_evl);
-          n_srv = want < sms - grid_evl ? want : sms - grid_evl;
+          n_srv = (want < sms - grid_evl ? want : sms - grid_evl) & ~1;  // even: see default_service_ctas
           if (3 * n_srv < want) n_srv = 0;  // too few would only make the warps wait (measured: 4 of 22 is a loss)
         } else {  // several waves: event-loop CTAs take turns on the SMs the service CTAs leave free, if that is faster
           int w = sms, srv = 0;

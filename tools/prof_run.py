@@ -17,6 +17,8 @@ topo, sv = genconfig.system_b(tab, 0.18, seed=1)
 p = tables.make_params(boxl=158.54, tstar=0.18, canon=True, n_replicas=R, engine=int(os.environ.get('DMDB_ENGINE', '1')))
 d = DMD(p, topo, tab, lib_path=os.environ.get('DMDB_LIB'))
 d.set_state(sv)
+if os.environ.get('DMDB_SVC'):
+    d.set_service_ctas(int(os.environ['DMDB_SVC']))
 d.run(warm)
 st = d.run(nev)
 print("R=%d events/replica=%d device_ms=%.2f events/s=%.3e" % (R, nev, st.device_ms, R * nev / (st.device_ms * 1e-3)))
