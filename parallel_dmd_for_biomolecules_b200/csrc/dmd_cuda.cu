@@ -334,6 +334,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, DMD_MIN_CTAS) dmd_event_lo
   evl::Warp::sync();
   if (evl::Warp::lane() == 0)
     for (int k = 0; k < 15; k++) atomicAdd(&evl::g_phase_cyc[k], r.prof[k]);
+  if ((threadIdx.x & 31) == 0) {  // when the CTA's last warp finished, and on which SM it ran
+    unsigned long long gt;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    atomicMax(&evl::g_cta_end[blockIdx.x], gt);
+    evl::g_cta_sm[blockIdx.x] = smid;
+  }
 #endif
   evl::rep_save(r);
   if (n_srv > 0 && evl::Warp::lane() == 0) atomicAdd(&d.svc_ctl[0], 1ull);  // the service CTAs leave when all warps are done
@@ -1161,6 +1169,22 @@ inline void run_op(const dmd::DevArrays& d, int op, int r0, int nrep, long long 
         for (int k = 0; k < 12; k++) tot += (double)c[k];
         for (int k = 0; k < 12; k++) fprintf(stderr, "phase %-16s %9.1f cycles/event  %5.1f %%\n", nm[k], c[k] / ev, 100.0 * c[k] / tot);
         fprintf(stderr, "phase total         %9.1f cycles/event\n", tot / ev);
+        {  // spread of the event-loop CTAs' finishing times (the launch ends with the last one)
+          static unsigned long long e[512];
+          static unsigned sm[512];
+          CUDA_OK(cudaMemcpyFromSymbol(e, evl::g_cta_end, sizeof(e)));
+          CUDA_OK(cudaMemcpyFromSymbol(sm, evl::g_cta_sm, sizeof(sm)));
+          unsigned long long lo = ~0ull, hi = 0;
+          for (int b = n_srv; b < grid_evl + n_srv && b < 512; b++) {
+            if (e[b] < lo) lo = e[b];
+            if (e[b] > hi) hi = e[b];
+          }
+          fprintf(stderr, "event-loop CTAs finish within %.3f ms of one another; (ms before the last one : SM)", (hi - lo) * 1e-6);
+          for (int b = n_srv; b < grid_evl + n_srv && b < 512; b++) fprintf(stderr, " %.1f:%u", (hi - e[b]) * 1e-6, sm[b]);
+          fprintf(stderr, "\n");
+          unsigned long long z[512] = {0};
+          CUDA_OK(cudaMemcpyToSymbol(evl::g_cta_end, z, sizeof(z)));
+        }
       }
 #endif
       if (n_srv > 0 && getenv("DMDB_DEBUG")) {

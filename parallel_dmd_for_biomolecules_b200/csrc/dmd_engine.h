@@ -42,6 +42,11 @@ constexpr int CQ_Q = CQ_CAP - 8;    // ... of CQ_Q entries (<= one per down-list
 #if defined(DMD_PHASE_PROF) && !defined(DMD_HOST_TRACE)
 __device__ unsigned long long g_phase_cyc[16];
 __device__ unsigned long long g_phase_acc[160 * 4 * 28 * 16];  // per-replica accumulators of the 8-lane build
+__device__ unsigned long long g_cta_end[512];
+__device__ unsigned g_cta_sm[512];
+#if DMD_PHASE_PROF == 2  // only the finishing times of the CTAs: the loop itself runs as in the product build
+#define DMD_PROF_MARK(r, k) do { } while (0)
+#else
 #define DMD_PROF_MARK(r, k)                                                    \
   do {                                                                         \
     if ((r).prof && Warp::lane() == 0) {                                       \
@@ -50,6 +55,7 @@ __device__ unsigned long long g_phase_acc[160 * 4 * 28 * 16];  // per-replica ac
       (r).prof[15] = now_;                                                     \
     }                                                                          \
   } while (0)
+#endif
 #else
 #define DMD_PROF_MARK(r, k) do { } while (0)
 #endif
