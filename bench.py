@@ -109,16 +109,22 @@ def measured_peak():
 
 
 def kernel_source_hash():
-    """sha-256 (first 16 hex digits) over the CUDA sources of the library: ties a measured DRAM-traffic figure to the
-    code it was captured from (the GPU box holds no .git)"""
+    """sha-256 (first 16 hex digits) over the CUDA sources of the library with comments and white space removed: ties a
+    measured DRAM-traffic figure to the CODE it was captured from (the GPU box holds no .git); editing a comment does
+    not invalidate a capture, editing a statement does"""
     import hashlib
+    import re
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, "parallel_dmd_for_biomolecules_b200", "csrc")
     for name in sorted(os.listdir(csrc)):
         if not name.endswith((".h", ".cu")):
             continue
-        with open(os.path.join(csrc, name), "rb") as f:
-            h.update(name.encode() + b"\0" + f.read())
+        with open(os.path.join(csrc, name), "r", encoding="utf-8", errors="replace") as f:
+            text = f.read()
+        text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)  # block comments
+        text = re.sub(r"//[^\n]*", " ", text)               # line comments (the sources hold no '//' inside string literals)
+        text = re.sub(r"\s+", " ", text)
+        h.update(name.encode() + b"\0" + text.encode())
     return h.hexdigest()[:16]
 
 

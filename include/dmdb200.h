@@ -80,7 +80,7 @@ typedef struct dmdb_params {
   int32_t device;       /* CUDA device ordinal */
   int32_t nbr_capacity; /* per-bead capacity of the up and of the down neighbour list (0 = default 64) */
   int32_t log_capacity; /* per-replica event-log capacity in events (0 = no log); logging stops when it is full */
-  int32_t engine;       /* event-loop engine: 0 = automatic, 1 = a group of lanes per replica, two replicas per warp (throughput: thousands of
+  int32_t engine;       /* event-loop engine: 0 = automatic, 1 = a group of lanes per replica, four replicas per warp (throughput: thousands of
                            replicas), 2 = one CTA per replica with batched conservative commit (latency: a few
                            trajectories; state resident in shared memory), 3 = the same batched commit with every round spread
                            over the whole GPU (one large system, e.g. 10^6 beads).  Results are bit-identical. */

@@ -1,23 +1,26 @@
-// dmd_lockstep.h -- two replicas per hardware warp, executed in LOCKSTEP (device only; included by dmd_cuda.cu right
-// after the 16-lane build of dmd_engine.h, inside the same namespace).
+// dmd_lockstep.h -- several replicas per hardware warp, executed in LOCKSTEP (device only; included by dmd_cuda.cu
+// right after the 8-lane (or 16-lane) build of dmd_engine.h, inside the same namespace).
 //
 // Why.  The warp-per-replica loop is bound by the latency of its dependent gathers and by instruction supply, not by
 // lanes or issue slots: a pass over the ~11 items of a bead leaves most of 32 lanes idle, the
 // register file limits an SM to 28 hardware warps, and 28 instruction streams at 28 different places thrash the 32 KB
-// instruction cache.  Giving a replica 16 lanes puts TWO replicas into one warp: twice the events in flight per
-// register, and ONE instruction stream (one fetch, one issue slot) serves both.
+// instruction cache.  Giving a replica LK_W = 8 lanes puts LK_SUB = 4 replicas into one warp (16 lanes: 2): four times
+// the events in flight per register, and ONE instruction stream (one fetch, one issue slot) serves all of them.
 //
-// How.  The 16-lane engine code of dmd_engine.h names the lanes of its own half in every collective, so the halves
-// of a warp may run it independently -- but a collective on half a warp splits the warp, and the halves then take
-// turns instead of sharing instructions (measured: no gain).  The functions below are the hot path -- calendar pop,
-// hard-core / bond event, partial_events -- rewritten so that both halves execute the SAME instructions at the same
-// time: every collective is a full-warp one (shuffles of width 16, full ballots read by halves, REDUX with the other
-// group's lanes neutralised) and every loop bound is a full-warp vote.  The rule that keeps this deadlock-free:
-// between two full-warp collectives the halves diverge only into code that has none (or into the serial 16-lane
-// engine, whose collectives name one half).  Whenever one of the two replicas has anything but a hard-core / bond
-// event at the head of its calendar (H-bond events, ghost, interval incl. list rebuild, output; a few per cent of
-// the events), BOTH process their event through the serial engine code and meet again at the next vote.
+// How.  The LK_W-lane engine code of dmd_engine.h names the lanes of its own segment in every collective, so the
+// segments of a warp may run it independently -- but a collective on part of a warp splits the warp, and the parts then
+// take turns instead of sharing instructions (measured: no gain).  The functions below are the hot path -- calendar
+// pop, hard-core / bond event, partial_events -- rewritten so that all replicas of the warp execute the SAME
+// instructions at the same time: every collective is a full-warp one (shuffles of width LK_W, full ballots read by
+// segments, butterfly minima inside the aligned 8-lane segment / REDUX with the other lanes neutralised in the 16-lane
+// build) and every loop bound is a full-warp vote.  The rule that keeps this deadlock-free: between two full-warp
+// collectives the replicas diverge only into code that has none (or into the serial LK_W-lane engine, whose
+// collectives name one segment).  A replica that has anything but a hard-core / bond event at the head of its calendar
+// (H-bond events, ghost, interval incl. list rebuild, output; ~1.6 % of the events) processes it through the serial
+// engine code in a divergent branch while the others wait; all meet again at the next vote.
 // Results are those of the serial code: same items, same order of compare-and-lower operations, same tie rules.
+// ("both replicas" / "half" in the comments below date from the 16-lane version: read "all replicas of the warp" /
+// "the replica's lane segment".)
 #if (DMD_W != 16 && DMD_W != 8) || defined(DMD_HOST_TRACE)
 #error "dmd_lockstep.h is the several-replicas-per-warp hot path: include it in the 16- or 8-lane device build only"
 #endif
@@ -451,7 +454,7 @@ DMD_DEV void lk_process(Rep& r, const int o, const CalEnt& ev) {
   lk_partial_events(r, pi, pj, xpulse_del, redo);  // main.F90:943, :1049
 }
 
-// run_events() for the two replicas of a hardware warp
+// run_events() for the replicas of a hardware warp
 DMD_DEV void lk_run_events(Rep& r, int64_t n_events, bool stop_at_output) {
   const int64_t coll_end = r.coll + n_events;
   bool live = r.error == 0;
