@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--replicas", type=int, default=0, help="replicas per GPU (0 = dmdb_device_fill: one 28-warp CTA (112 replicas) per "
-                    "SM minus the list-rebuild service CTAs, 13888 on a 148-SM B200)")
+                    "SM minus the list-rebuild service CTAs, 14112 on a 148-SM B200)")
     ap.add_argument("--events", type=int, default=20000, help="calendar events per replica per step")
     ap.add_argument("--ref-events", type=int, default=400000, help="events per host thread per step (--impl reference)")
     ap.add_argument("--ladder", action="store_true", help="config 3 on one GPU too: 11-temperature ladders + exchange per step "
@@ -253,7 +253,7 @@ def aggregated_regime(tab, peak):
     boxl = float(fx["boxl"])
     topo, _ = genconfig.system_b(tab, TSTAR, seed=1, boxl=boxl)
     # an aggregated box rebuilds its lists ~5 x slower than a dilute one (a bead has many more candidates): the measured
-    # optimum is 48 list-rebuild service CTAs beside 100 event-loop CTAs (tools/aggr_run.py: 40: 0.95e8, 44: 1.13e8, 48: 1.44e8, 52: 1.38e8, 56: 1.31e8) (24 / 124 for the dilute headline)
+    # optimum is 48 list-rebuild service CTAs beside 100 event-loop CTAs (tools/aggr_run.py: 40: 0.95e8, 44: 1.13e8, 48: 1.44e8, 52: 1.38e8, 56: 1.31e8) (22 / 126 for the dilute headline)
     import torch
     service = 48
     fill_r, fill_s = device_fill(0)

@@ -196,8 +196,13 @@ int dmdb_create(const dmdb_params* p, const dmdb_topology* topo, const dmdb_tabl
     be::zero(d.blkstat, R * 16 * sizeof(long long));
     d.svc_flag = dalloc<int32_t>(h.get(), R);
     be::zero(d.svc_flag, R * 4);
-    d.svc_ctl = dalloc<unsigned long long>(h.get(), dmd::SVC_CTL_WORDS);
-    be::zero(d.svc_ctl, dmd::SVC_CTL_WORDS * 8);
+    {
+      const size_t qcap = 2 * (size_t)R + 64, words = dmd::SVC_Q_RING + qcap;
+      d.svc_ctl = dalloc<unsigned long long>(h.get(), words);
+      be::zero(d.svc_ctl, words * 8);
+      const unsigned long long cap_word = qcap;
+      be::h2d(d.svc_ctl + dmd::SVC_Q_CAP, &cap_word, 8);
+    }
     h->eout = dalloc<dmd::OutRec>(h.get(), R);
     h->temp_buf = dalloc<double>(h.get(), R);
     be::zero(d.nup, R * N * 2);

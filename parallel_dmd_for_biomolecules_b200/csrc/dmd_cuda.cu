@@ -139,7 +139,7 @@ struct alignas(16) EvlSmem {
 #endif
 __device__ __forceinline__ void svc_group_sync(int grp, int gsz) { asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(gsz) : "memory"); }
 
-__device__ __noinline__ void svc_serve_in_kernel(DevArrays d, int r0, int nrep, unsigned char* scratch, size_t scratch_bytes) {
+__device__ __noinline__ void svc_serve_in_kernel(DevArrays d, int r0, int nrep, int n_srv, unsigned char* scratch, size_t scratch_bytes) {
   __shared__ int s_pick[DMD_SVC_GROUPS], s_state[DMD_SVC_GROUPS];
   const evl::Staged tab = evl::staged_global(d);
   const int gsz = ((int)blockDim.x / 32 / DMD_SVC_GROUPS) * 32;  // threads per group (whole warps)
@@ -152,64 +152,40 @@ __device__ __noinline__ void svc_serve_in_kernel(DevArrays d, int r0, int nrep, 
   int32_t* const s_heads = reinterpret_cast<int32_t*>(scratch);
   int32_t* const s_cnext = s_heads + d.ncc3;
   uint32_t* const s_cpk = reinterpret_cast<uint32_t*>(s_cnext + d.n_beads);
-  // Every group looks for requests in CIRCULAR order from its own starting point and takes the first one it meets, so
-  // that idle groups go for different requests (all of them taking the lowest pending index made them collide on one
-  // request and rescan).  Four flags per load, all loads of a thread in flight together.
-  const int32_t* const flags = d.svc_flag + r0;
-  const bool vec_ok = (reinterpret_cast<uintptr_t>(flags) & 15) == 0;
-  const int nvec = vec_ok ? nrep >> 2 : 0;
-  const int scan0 = nvec ? (int)(((long long)(blockIdx.x * DMD_SVC_GROUPS + grp) * nvec) / ((int)gridDim.x * DMD_SVC_GROUPS)) : 0;
+  // Which request a free group takes: the OLDEST one.  Requesters queue their replica index in a ticket ring
+  // (svc_request, dmd_types.h: SVC_Q_*); thread 0 of a free group claims the next ticket and reads its slot.  One pool,
+  // first come first served: no scan of the request words, no collisions, nobody is passed over.  (Measured before:
+  // every group scanning for the lowest pending index -- collisions, mean wait 560 us; scanning from a fixed point per
+  // group -- the far end of the array starved, 0.15 % of the requests waited more than the 40 ms after which the warp
+  // rebuilds in place; a stretch per group -- no pooling, mean wait 1100 us.)
+  unsigned long long* const rq = d.svc_ctl;
   while (true) {
-    if (tid == 0) s_pick[grp] = 0x7fffffff;
-    svc_group_sync(grp, gsz);
-    int found = 0x7fffffff;  // circular offset of the first pending request this thread saw
-    for (int k0 = tid; k0 < nvec; k0 += 4 * nt) {
-      int4 w[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        int v = k0 + u * nt + scan0;
-        v = v < nvec ? v : v - nvec;
-        w[u] = k0 + u * nt < nvec ? __ldcv(reinterpret_cast<const int4*>(flags) + v) : make_int4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int u = 3; u >= 0; u--) {
-        const int kb = (k0 + u * nt) * 4;
-        if (w[u].w == 1) found = kb + 3;
-        if (w[u].z == 1) found = kb + 2;
-        if (w[u].y == 1) found = kb + 1;
-        if (w[u].x == 1) found = kb;
-      }
-      if (found != 0x7fffffff) break;
-    }
-    if (found == 0x7fffffff)
-      for (int k = nvec * 4 + tid; k < nrep; k += nt)  // the last nrep % 4 flags (or all of them: unaligned array)
-        if (*(volatile const int32_t*)(flags + k) == 1) {
-          found = k;
-          break;
-        }
-    if (found != 0x7fffffff) atomicMin(&s_pick[grp], found);
-    svc_group_sync(grp, gsz);
-    int pick = s_pick[grp];
-    if (pick != 0x7fffffff && pick < nvec * 4) {  // circular offset -> replica
-      int v = (pick >> 2) + scan0;
-      v = v < nvec ? v : v - nvec;
-      pick = v * 4 + (pick & 3);
-    }
     if (tid == 0) {
-      if (pick == 0x7fffffff) {
-        const unsigned long long done = *(volatile unsigned long long*)&d.svc_ctl[0];
-        s_state[grp] = done >= (unsigned long long)nrep ? 2 : 0;
-        if (s_state[grp] == 0) __nanosleep(1000);
+      int state = 0, pick = 0;
+      const unsigned long long hd = evl::svc_ld_relaxed64(&rq[SVC_Q_HEAD]), tl = evl::svc_ld_relaxed64(&rq[SVC_Q_TAIL]);
+      if (hd < tl) {
+        if (atomicCAS(&rq[SVC_Q_HEAD], hd, hd + 1ull) == hd) {  // ticket hd is this group's
+          const unsigned long long* const slot = &rq[SVC_Q_RING + hd % rq[SVC_Q_CAP]];
+          unsigned long long e = evl::svc_ld_acquire64(slot);
+          while ((e >> 24) != hd + 1ull) e = evl::svc_ld_acquire64(slot);  // (written right after the ticket was taken)
+          pick = (int)(e & 0xffffffull);
+          state = evl::svc_cas_acq_rel(d.svc_flag + pick, 1, 2) == 1 ? 1 : 0;  // 0: taken back by its warp meanwhile
+        }
       } else {
-        s_state[grp] = evl::svc_cas_acq_rel(d.svc_flag + r0 + pick, 1, 2) == 1 ? 1 : 0;
+        const unsigned long long done = *(volatile unsigned long long*)&d.svc_ctl[0];
+        state = done >= (unsigned long long)nrep ? 2 : 0;
+        if (state == 0) __nanosleep(500);
       }
+      s_pick[grp] = pick;
+      s_state[grp] = state;
     }
     svc_group_sync(grp, gsz);
-    const int state = s_state[grp];
+    const int pick = s_pick[grp], state = s_state[grp];
+    svc_group_sync(grp, gsz);  // (thread 0 writes both again at the top of the loop)
     if (state == 2) return;
     if (state == 0) continue;
     const long long t0 = clock64();
-    const int rid = r0 + pick;
+    const int rid = pick;  // (the queue carries indices into the request words of the whole replica set)
     evl::Rep q;
     evl::rep_bind(q, d, tab, nullptr, rid);  // scalars as saved by the requesting warp (tfalse = 0, new interval_max)
     q.error = 0;
@@ -291,7 +267,7 @@ __device__ __noinline__ void svc_serve_in_kernel(DevArrays d, int r0, int nrep, 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, DMD_MIN_CTAS) dmd_event_loop_kernel(DevArrays d, int r0, int nrep, long long n_events, int flags, int n_srv) {
   __shared__ EvlSmem sm;
   if ((int)blockIdx.x < n_srv) {
-    svc_serve_in_kernel(d, r0, nrep, reinterpret_cast<unsigned char*>(&sm), sizeof(EvlSmem));
+    svc_serve_in_kernel(d, r0, nrep, n_srv, reinterpret_cast<unsigned char*>(&sm), sizeof(EvlSmem));
     return;
   }
   const evl::Staged tab = stage_consts_t<evl::Staged>(d, &sm.consts);
@@ -307,6 +283,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, DMD_MIN_CTAS) dmd_event_lo
   if (n_srv > 0) {
     r.svc = d.svc_flag + rid;
     r.svc_ctl = d.svc_ctl;
+    r.svc_id = rid;
   }
 #if defined(DMD_PHASE_PROF)
 #if DMD_EVL_W >= 16
@@ -941,16 +918,17 @@ inline int sm_count() {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   return sms;
 }
-// one service CTA per 6.4 event-loop CTAs with one or two replicas per warp, per 5.2 with four (an event-loop CTA then
-// processes ~1.5 x the events and asks for as many more rebuilds): 124 + 24 CTAs on a 148-SM B200.  Measured on the
-// headline workload (tools/prof_run.py, 40 000 events per replica after 60 000): 20: 2.36e8, 23: 2.78e8, 24: 3.09e8,
-// 25: 2.80e8, 26: 3.05e8, 27: 2.84e8, 28: 3.01e8, 30: 2.98e8 events/s.  Too few service CTAs cost far more than too many
-// (requests queue up, time out and are rebuilt in place), and the count must be EVEN: the two SMs of a TPC get
-// consecutive CTAs, an odd count puts one event-loop CTA next to a service CTA, that CTA runs ~9 % slower than the
-// others (it shares the TPC's instruction cache with the rebuild code) and the launch ends when the last CTA does.
+// one service CTA per 6.4 event-loop CTAs with one or two replicas per warp, per 5.7 with four (an event-loop CTA then
+// processes ~1.5 x the events and asks for as many more rebuilds): 126 + 22 CTAs on a 148-SM B200.  Measured on the
+// headline workload (tools/prof_run.py, 40 000 events per replica after 60 000): 16: 2.70e8, 18: 2.99e8, 20: 3.21e8,
+// 22: 3.19e8, 24: 3.13e8, 26: 3.12e8, 28: 3.06e8 events/s; the ladder workload of bench.py --ladder (every replica
+// restarts its lists at every exchange) 20: 2.97e8, 24: 3.01e8.  Below ~20 the service saturates and the warps queue.
+// The count must be EVEN: the two SMs of a TPC get consecutive CTAs, an odd count puts one event-loop CTA next to a
+// service CTA, that CTA runs ~9 % slower than the others (it shares the TPC's instruction cache with the rebuild code)
+// and the launch ends when the last CTA does (measured: 23: 2.78e8, 24: 3.09e8, 25: 2.80e8, 26: 3.05e8).
 inline int default_service_ctas(int worker_ctas) {
   if (worker_ctas < 32) return 0;
-  return ((dmd::EVL_RPW >= 4 ? (worker_ctas * 25 + 64) / 128 : (worker_ctas * 10 + 32) / 64) + 1) & ~1;
+  return ((dmd::EVL_RPW >= 4 ? (worker_ctas * 22 + 64) / 128 : (worker_ctas * 10 + 32) / 64) + 1) & ~1;
 }
 inline void device_fill(int& replicas, int& service) {
   const int sms = sm_count();

@@ -80,7 +80,8 @@ struct Rep {
   OutRec* out;
   int32_t* cq;  // cascade queue storage (shared memory on the device)
   int32_t* svc;  // this replica's request word of the list-rebuild service, or nullptr: rebuild in place
-  unsigned long long* svc_ctl;  // service counters ([2] requests taken back, [3] cycles spent waiting)
+  unsigned long long* svc_ctl;  // service counters ([2] requests taken back, [3] cycles spent waiting) and request queue
+  int32_t svc_id;               // the replica's index in the request words (what the request queue carries)
   // scalars cached in registers (identical in every lane)
   double t, tfalse, old_tfalse, setemp, interval, t_fact, interval_max, n_forced, avegtime;
   int64_t coll;
@@ -172,6 +173,7 @@ DMD_DEV void rep_bind(Rep& r, const DevArrays& d, const Staged& st, int32_t* cq,
   }
   r.svc = nullptr;
   r.svc_ctl = nullptr;
+  r.svc_id = 0;
   rep_load_scalars(r);
 }
 
@@ -1746,6 +1748,17 @@ DMD_DEV int svc_ld_relaxed(const int32_t* p) {  // polling: no L1 invalidation (
 }
 DMD_DEV void svc_fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 DMD_DEV void svc_st_release(int32_t* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+DMD_DEV void svc_st_release64(unsigned long long* p, unsigned long long v) { asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+DMD_DEV unsigned long long svc_ld_acquire64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+DMD_DEV unsigned long long svc_ld_relaxed64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 DMD_DEV int svc_cas_acq_rel(int32_t* p, int cmp, int val) {
   int old;
   asm volatile("atom.acq_rel.gpu.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
@@ -1758,6 +1771,11 @@ DMD_COLD bool svc_request(Rep r) {
   int res = 0;  // 0 served, 1 in place, 2 time-out
   if (Warp::lane() == 0) {
     svc_st_release(r.svc, 1);
+    {  // queue the request: ticket, then the tagged slot (release: whoever reads the slot also sees the word above)
+      unsigned long long* const q = r.svc_ctl;
+      const unsigned long long tk = atomicAdd(&q[SVC_Q_TAIL], 1ull);
+      svc_st_release64(&q[SVC_Q_RING + tk % q[SVC_Q_CAP]], ((tk + 1ull) << 24) | (unsigned long long)(unsigned)r.svc_id);
+    }
     const long long t0 = clock64();
     while (true) {
       const int v = svc_ld_relaxed(r.svc);

@@ -201,8 +201,14 @@ struct DevArrays {
   // neighbour-list + calendar rebuilds for the warps of all other CTAs, so that the event-loop SMs keep only the
   // hot loop in their 32 KB instruction caches)
   int32_t* svc_flag;      // per replica: 0 idle, 1 rebuild requested, 2 being served, 3 taken back by its own warp
-  unsigned long long* svc_ctl;  // [0] finished worker warps [1] rebuilds served [2] requests taken back [3] wait cycles [4] service cycles
+  unsigned long long* svc_ctl;  // [0] finished worker warps [1] rebuilds served [2] requests taken back [3] wait cycles [4] service cycles;
+                                // from SVC_Q_HEAD on: the request queue (below)
 };
-constexpr int SVC_CTL_WORDS = 8;
+constexpr int SVC_CTL_WORDS = 8;  // counters, cleared before every launch
+// behind them, never cleared: the FIFO of pending requests.  A requester takes a ticket (SVC_Q_TAIL), writes
+// (ticket + 1) << 24 | replica into slot ticket % capacity; a free service group claims the next ticket (SVC_Q_HEAD) and
+// reads the slot once its tag says it is written.  The capacity is at least twice the replica count and a replica has
+// one request outstanding at most, so a slot is read long before it can come round again.
+constexpr int SVC_Q_HEAD = 8, SVC_Q_TAIL = 9, SVC_Q_CAP = 10, SVC_Q_RING = 16;
 
 }  // namespace dmd
