@@ -253,9 +253,9 @@ def aggregated_regime(tab, peak):
     boxl = float(fx["boxl"])
     topo, _ = genconfig.system_b(tab, TSTAR, seed=1, boxl=boxl)
     # an aggregated box rebuilds its lists ~5 x slower than a dilute one (a bead has many more candidates): the measured
-    # optimum is 48 list-rebuild service CTAs beside 100 event-loop CTAs (tools/aggr_run.py: 40: 0.95e8, 44: 1.13e8, 48: 1.44e8, 52: 1.38e8, 56: 1.31e8) (22 / 126 for the dilute headline)
+    # optimum is 44 list-rebuild service CTAs beside 104 event-loop CTAs (tools/aggr_run.py: 36: 1.26e8, 40: 1.38e8, 44: 1.48e8, 48: 1.45e8) (22 / 126 for the dilute headline)
     import torch
-    service = 48
+    service = 44
     fill_r, fill_s = device_fill(0)
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     R = (sms - service) * (fill_r // (sms - fill_s))  # replicas per event-loop CTA as dmdb_device_fill sizes them
