@@ -1731,8 +1731,9 @@ DMD_DEV void sorted_grid_lists(Rep& r, SortedGrid g, int warp, int nwarps) {
 }
 
 // ---- list-rebuild service (device only).  A warp whose replica needs nbor() + events() publishes the request
-// in its svc word and sleeps; a service CTA on another SM claims it (1 -> 2), rebuilds with all its threads and
-// clears the word.  release/acquire at gpu scope on the word orders the replica's arrays between the two SMs (the
+// in its svc word, queues its index in the ticket ring behind the service counters (dmd_types.h: SVC_Q_*) and sleeps;
+// a free group of a service CTA on another SM claims the oldest ticket and the word (1 -> 2), rebuilds with all its
+// threads and clears the word.  release/acquire at gpu scope on the word orders the replica's arrays between the two SMs (the
 // acquire also drops the stale L1 lines).  A request nobody claims within SVC_PATIENCE cycles is taken back
 // (1 -> 3) and served in place, so the loop never depends on a service CTA being resident.
 #ifndef DMD_SVC_PATIENCE
