@@ -206,8 +206,10 @@ int dmdb_exchange_gathered(dmdb_handle* h, const double* gathered, int world, in
 /* The pieces, for a host that wants to decide itself: potential energies of the local replicas ... */
 int dmdb_potential_energies(dmdb_handle* h, double* epot /* n_replicas */, double* tstar /* n_replicas */);
 /* ... and the temperature change: replicas whose entry differs from their current T* have their velocities
- * rescaled by sqrt(T_new/T_old), their time constants reset (main.F90:143-156) and lists + calendar rebuilt, all
- * on the device; H-bond state is kept.  Entries <= 0 leave the replica untouched. */
+ * rescaled by sqrt(T_new/T_old), their time constants reset (main.F90:143-156) and their calendar re-derived, all
+ * on the device; neighbour lists (still valid: positions do not change) and H-bond state are kept.  Entries <= 0
+ * leave the replica untouched.  (dmdb_set_temperature is the other temperature change: a restart as the reference
+ * would do it between two runs.) */
 int dmdb_apply_temperatures(dmdb_handle* h, const double* tstar_new /* n_replicas */);
 
 

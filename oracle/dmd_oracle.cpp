@@ -1390,8 +1390,9 @@ void Oracle::set_temperature(double tstar) {
 }
 
 // Replica-exchange temperature change on resident state.  NOT in the reference: defined here and
-// in the engine identically -- true positions, velocities scaled by sqrt(T_new/T_old), time constants of
-// main.F90:143-156 reset, lists and calendar rebuilt, H-bond state kept.
+// in the engine identically -- true positions (not wrapped), velocities scaled by sqrt(T_new/T_old), time constants of
+// main.F90:143-156 reset, calendar re-derived; the neighbour lists and the positions they were built at (old_r*) are
+// kept (positions do not change, so the lists stay valid), H-bond state kept.
 void Oracle::retemp(double tstar_new) {
   const int N = noptotal;
   const double tf = tfalse;
@@ -1399,11 +1400,9 @@ void Oracle::retemp(double tstar_new) {
   const double scale = std::sqrt(setemp_new / setemp);
   t = t + tf;
   for (int k = 1; k <= N; k++) {
-    double x = S(1, k) + S(4, k) * tf, y = S(2, k) + S(5, k) * tf, z = S(3, k) + S(6, k) * tf;
-    x = x - dnint(x); y = y - dnint(y); z = z - dnint(z);
+    const double x = S(1, k) + S(4, k) * tf, y = S(2, k) + S(5, k) * tf, z = S(3, k) + S(6, k) * tf;
     S(1, k) = x; S(2, k) = y; S(3, k) = z;
     S(4, k) = S(4, k) * scale; S(5, k) = S(5, k) * scale; S(6, k) = S(6, k) * scale;
-    old_rx[k] = x; old_ry[k] = y; old_rz[k] = z;
   }
   tfalse = 0.0; old_tfalse = 0.0;
   setemp = setemp_new;
@@ -1422,7 +1421,6 @@ void Oracle::retemp(double tstar_new) {
   tim[N + 1] = tg;
   tim[N + 2] = interval;
   tim[N + 3] = 3.3 / (std::sqrt(setemp)) + 5;
-  nbor();
   for (int k = 1; k <= N; k++) { tim[k] = interval_max + ltstep; coltype[k] = -1; nptnr[k] = -1; }
   events();
 }

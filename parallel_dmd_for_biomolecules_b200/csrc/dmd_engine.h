@@ -2062,7 +2062,11 @@ DMD_DEV void run_events(Rep& r, int64_t n_events, bool stop_at_output) {
 
 // Replica-exchange temperature change on resident state (new functionality): advance to true
 // positions, rescale velocities by sqrt(T_new/T_old), reset the time constants of main.F90:143-156 for the new
-// temperature and rebuild lists + calendar.  H-bond state (bptnr, identity, extra_repuls, overlay) is kept.
+// temperature and re-derive the calendar.  The neighbour lists are KEPT: positions do not change, so the lists stay
+// valid -- the positions they were built at (oldr) stay the reference of the displacement test (displ.f), and the
+// positions are not wrapped here for the same reason (the interval event wraps when it rebuilds).  Rebuilding the
+// lists of every swapped replica at the same moment also made their next rebuild requests arrive in one burst.
+// H-bond state (bptnr, identity, extra_repuls, overlay) is kept.
 DMD_DEV void retemp(Rep& r, double tstar_new) {
   const int N = r.N;
   const double tf = r.tfalse;
@@ -2072,11 +2076,9 @@ DMD_DEV void retemp(Rep& r, double tstar_new) {
   Warp::sync();
   for (int k = Warp::lane(); k < N; k += DMD_W) {
     BeadRec* p = &r.rec[k];
-    double x = p->x + p->vx * tf, y = p->y + p->vy * tf, z = p->z + p->vz * tf;
-    x = x - dmd_round(x); y = y - dmd_round(y); z = z - dmd_round(z);
+    const double x = p->x + p->vx * tf, y = p->y + p->vy * tf, z = p->z + p->vz * tf;
     p->x = x; p->y = y; p->z = z;
     p->vx = p->vx * scale; p->vy = p->vy * scale; p->vz = p->vz * scale;
-    r.oldr[3 * k] = x; r.oldr[3 * k + 1] = y; r.oldr[3 * k + 2] = z;
   }
   r.tfalse = 0.0;
   r.old_tfalse = 0.0;
@@ -2099,7 +2101,6 @@ DMD_DEV void retemp(Rep& r, double tstar_new) {
     r.cal[N + 2].t = 3.3 / (dmd_sqrt(r.setemp)) + 5;
   }
   Warp::sync();
-  nbor(r);
   predict_all(r);
 }
 

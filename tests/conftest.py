@@ -46,12 +46,14 @@ def hosttrace_lib():
     return HOSTTRACE
 
 
-def compare_engines(ora, dev, replica=0, n_events=0, time_rtol=1e-12):
+def compare_engines(ora, dev, replica=0, n_events=0, time_rtol=1e-12, cells=True):
     """The parity surface of BASELINE.json's north_star: bit-exact cells / neighbour sets / next-event partner and
     type, event times within 1e-12 relative, identical committed-event sequence.  The engine is held to more than
     the stated tolerance: every time and every state double must be BIT-EQUAL to the oracle's (array_equal), so that
     a 1-ulp drift cannot hide behind the tolerance."""
-    assert np.array_equal(ora.cells(), dev.cells(replica)), "cell assignment"
+    if cells:  # (the engine reports the cells of its last list rebuild, the oracle those of the current positions:
+        #    comparable right after a rebuild only)
+        assert np.array_equal(ora.cells(), dev.cells(replica)), "cell assignment"
     for down in (False, True):
         a, b = ora.nbors(down), dev.nbors(replica, down)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), "neighbour lists (down=%s)" % down
