@@ -167,9 +167,15 @@ __device__ __noinline__ void svc_serve_in_kernel(DevArrays d, int r0, int nrep, 
         if (atomicCAS(&rq[SVC_Q_HEAD], hd, hd + 1ull) == hd) {  // ticket hd is this group's
           const unsigned long long* const slot = &rq[SVC_Q_RING + hd % rq[SVC_Q_CAP]];
           unsigned long long e = evl::svc_ld_acquire64(slot);
-          while ((e >> 24) != hd + 1ull) e = evl::svc_ld_acquire64(slot);  // (written right after the ticket was taken)
-          pick = (int)(e & 0xffffffull);
-          state = evl::svc_cas_acq_rel(d.svc_flag + pick, 1, 2) == 1 ? 1 : 0;  // 0: taken back by its warp meanwhile
+          const long long t0 = clock64();  // (the slot is written right after the ticket was taken: a short wait)
+          while ((e >> 24) < hd + 1ull && clock64() - t0 < evl::SVC_TIMEOUT) e = evl::svc_ld_acquire64(slot);
+          if ((e >> 24) == hd + 1ull) {
+            pick = (int)(e & 0xffffffull);
+            state = evl::svc_cas_acq_rel(d.svc_flag + pick, 1, 2) == 1 ? 1 : 0;  // 0: taken back by its warp meanwhile
+          }
+          // else: a later lap of the ring has overwritten the slot -- more than SVC_Q_CAP tickets were outstanding,
+          // which takes a service so far behind that the tickets of requests taken back pile up -- or it was never
+          // written.  The ticket is skipped; if its request is still pending, its warp takes it back after SVC_PATIENCE
         }
       } else {
         const unsigned long long done = *(volatile unsigned long long*)&d.svc_ctl[0];

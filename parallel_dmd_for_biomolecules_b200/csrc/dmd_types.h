@@ -207,8 +207,10 @@ struct DevArrays {
 constexpr int SVC_CTL_WORDS = 8;  // counters, cleared before every launch
 // behind them, never cleared: the FIFO of pending requests.  A requester takes a ticket (SVC_Q_TAIL), writes
 // (ticket + 1) << 24 | replica into slot ticket % capacity; a free service group claims the next ticket (SVC_Q_HEAD) and
-// reads the slot once its tag says it is written.  The capacity is at least twice the replica count and a replica has
-// one request outstanding at most, so a slot is read long before it can come round again.
+// reads the slot once its tag says it is written.  A replica has one request outstanding at most and the capacity is
+// twice the replica count, so a slot normally is read long before it comes round again; only the tickets of requests
+// that were taken back (they stay queued and are skipped when claimed) can pile up behind a service that is far too
+// slow -- a group that finds a LATER tag in its slot skips the ticket (tests/test_service_queue_model.py).
 constexpr int SVC_Q_HEAD = 8, SVC_Q_TAIL = 9, SVC_Q_CAP = 10, SVC_Q_RING = 16;
 
 }  // namespace dmd
